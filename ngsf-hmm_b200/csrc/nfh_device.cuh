@@ -1,0 +1,126 @@
+// nfh_device.cuh - device-side building blocks shared by the hot-path kernels.
+//
+// The two-state HMM of ngsF-HMM (shared/HMM.cpp) has, at site s, the transition
+//   T_s[k][l] = (1 - c_s) * q_l + [k == l] * c_s,   c_s = exp(-alpha * d_s)   (HMM.cpp:130-139)
+// with q = (1 - F, F).  The reference runs forward/backward/Viterbi in log
+// space, site by site.  Here the recursions run in SCALED LINEAR space as
+// products of 2x2 matrices  M_s = T_s * diag(1, r_s)  where r_s = e1/e0 is the
+// ratio of the two state emissions (the common factor e0 only adds
+// sum_s log e0 to the log-likelihood and cancels in the posterior), so that a
+// whole individual becomes a chunked associative scan.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfh {
+
+constexpr int kSitesPerThread = 8;                       // contiguous sites owned by one thread
+constexpr int kScanThreads = 256;                        // threads per CTA in the scan kernels
+constexpr int kTile = kSitesPerThread * kScanThreads;    // 2048 sites per CTA tile
+constexpr double kLn2 = 0.693147180559945309417232121458;
+constexpr double kEps = 1e-5;                            // EPSILON, gen_func.hpp:16
+constexpr unsigned kFull = 0xffffffffu;
+
+enum : int { kFlagNaN = 1, kFlagFwBw = 2 };
+
+struct M2 {  // row-major [[a b] [c d]], acts on row vectors from the left: v' = v * M
+  double a, b, c, d;
+};
+
+__device__ __forceinline__ M2 matmul(const M2 &x, const M2 &y) {
+  M2 r;
+  r.a = fma(x.a, y.a, x.b * y.c);
+  r.b = fma(x.a, y.b, x.b * y.d);
+  r.c = fma(x.c, y.a, x.d * y.c);
+  r.d = fma(x.c, y.b, x.d * y.d);
+  return r;
+}
+
+// 2^e as a double, e clamped to the normal range.
+__device__ __forceinline__ double pow2i(int e) {
+  e = max(-1000, min(1000, e));
+  return __hiloint2double((1023 + e) << 20, 0);
+}
+
+// Exponent (floor(log2)) of a non-negative double from its bit pattern;
+// 0 for zero/subnormal/inf/NaN so that those are left untouched.
+__device__ __forceinline__ int exponent_of(double m) {
+  int be = (__double2hiint(m) >> 20) & 0x7ff;
+  return (be == 0 || be == 0x7ff) ? 0 : max(-1000, min(1000, be - 1023));
+}
+
+// Scale a non-negative matrix so its largest entry lies in [1, 2); returns the
+// removed power of two (exact: multiplication by 2^-e does not round).
+__device__ __forceinline__ int renorm(M2 &m) {
+  int e = exponent_of(fmax(fmax(m.a, m.b), fmax(m.c, m.d)));
+  double s = pow2i(-e);
+  m.a *= s; m.b *= s; m.c *= s; m.d *= s;
+  return e;
+}
+
+__device__ __forceinline__ int renorm2(double &x, double &y) {
+  int e = exponent_of(fmax(x, y));
+  double s = pow2i(-e);
+  x *= s; y *= s;
+  return e;
+}
+
+// Right-multiply M by the site matrix M_s = T_s diag(1, r):
+//   row (x0, x1) -> ( c x0 + (x0+x1) g0 ,  (c x1 + (x0+x1) g1) r ),  g_l = (1-c) q_l
+__device__ __forceinline__ void apply_site(M2 &m, double c, double g0, double g1, double r) {
+  double s0 = m.a + m.b, s1 = m.c + m.d;
+  double a = fma(c, m.a, s0 * g0);
+  double b = fma(c, m.b, s0 * g1) * r;
+  double cc = fma(c, m.c, s1 * g0);
+  double d = fma(c, m.d, s1 * g1) * r;
+  m.a = a; m.b = b; m.c = cc; m.d = d;
+}
+
+__device__ __forceinline__ M2 site_matrix(double c, double g0, double g1, double r) {
+  M2 m;
+  m.a = g0 + c; m.b = g1 * r;
+  m.c = g0;     m.d = (g1 + c) * r;
+  return m;
+}
+
+__device__ __forceinline__ M2 identity2() { M2 m; m.a = 1; m.b = 0; m.c = 0; m.d = 1; return m; }
+
+__device__ __forceinline__ M2 shfl_down_m(const M2 &m, int off) {
+  M2 r;
+  r.a = __shfl_down_sync(kFull, m.a, off); r.b = __shfl_down_sync(kFull, m.b, off);
+  r.c = __shfl_down_sync(kFull, m.c, off); r.d = __shfl_down_sync(kFull, m.d, off);
+  return r;
+}
+__device__ __forceinline__ M2 shfl_up_m(const M2 &m, int off) {
+  M2 r;
+  r.a = __shfl_up_sync(kFull, m.a, off); r.b = __shfl_up_sync(kFull, m.b, off);
+  r.c = __shfl_up_sync(kFull, m.c, off); r.d = __shfl_up_sync(kFull, m.d, off);
+  return r;
+}
+
+// Ordered product over the warp: lane 0 ends with P_0 P_1 ... P_31 (and the sum
+// of exponents).  Other lanes hold partial results.
+__device__ __forceinline__ void warp_ordered_product(M2 &m, int &e) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    M2 o = shfl_down_m(m, off);
+    int oe = __shfl_down_sync(kFull, e, off);
+    if ((lane & (2 * off - 1)) == 0) {
+      m = matmul(m, o);
+      e += oe + renorm(m);
+    }
+  }
+}
+
+// Address of (individual row, site) in the site-blocked layout
+// [n_ranks][n_ind_local][site_block]; a tile never straddles a block because
+// site_block is a multiple of kTile.
+__device__ __forceinline__ size_t blocked_index(uint64_t row, uint64_t site, uint64_t n_rows, uint64_t site_block) {
+  uint64_t blk = site / site_block;
+  uint64_t off = site - blk * site_block;
+  return (size_t) ((blk * n_rows + row) * site_block + off);
+}
+
+}  // namespace nfh

@@ -1,0 +1,77 @@
+// nfh_kernels.h - host-visible launch interfaces of the CUDA kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nfh {
+
+constexpr int kMaxPoints = 5;   // objective points per individual per round: x, x -/+ eh_F, x -/+ eh_alpha (bfgs.cpp:22-43)
+
+struct TileProd {   // scaled 2x2 product of one tile: [[a b][c d]] * 2^e
+  double a, b, c, d, e;
+};
+
+struct LklGroup {   // objective requests of one individual sharing one read of its emissions
+  int ind;
+  int npts;
+  double F[kMaxPoints];
+  double alpha[kMaxPoints];
+  int out[kMaxPoints];
+};
+
+struct EstepArgs {
+  const double *emis;        // emission ratio, blocked [n_ranks][n_rows][site_block]
+  const double *dist;        // [n_ranks * site_block] Mb
+  const double *indF, *alpha;
+  const double *loge0_sum;   // [n_rows] sum over sites of log e0
+  TileProd *tile_prod;       // [n_rows][n_tiles]
+  double2 *fwd_carry, *bwd_carry;
+  double *post;              // blocked like emis
+  double *ind_lkl;
+  int *status;
+  uint64_t n_rows, n_rows_valid, n_sites, site_block;
+  uint32_t n_tiles;
+};
+
+struct LklArgs {
+  const double *emis, *dist, *loge0_sum;
+  const LklGroup *groups;
+  TileProd *tile_prod;       // [n_groups][kMaxPoints][n_tiles]
+  double *neg_lkl;
+  uint64_t n_rows, n_sites, site_block;
+  uint32_t n_tiles, n_groups;
+};
+
+struct FreqArgs {
+  const double *gl0, *gl1, *gl2;  // linear GL planes [n_ind_pad][site_block]
+  const double *post;             // [n_ind_pad][site_block] posterior of IBD state (or NULL: F_i = 0)
+  double *freq;                   // [site_block]
+  double *emis;                   // out: e1/e0  [n_ind_pad][site_block]
+  double *e0;                     // out: e0 or NULL
+  double *loge0_part;             // out: [gridDim.x][n_ind_pad] partial sums of log e0
+  uint64_t n_ind, n_ind_pad, site_block, sites_owned;
+  int update_freq;                // 1: run est_maf; 0: keep freq
+};
+
+struct ViterbiArgs {
+  const double *emis, *e0, *dist, *indF, *alpha;
+  unsigned char *work;            // [n_rows][n_sites_pad] back-pointer bytes, overwritten with the path
+  uint64_t n_rows, n_rows_valid, n_sites, site_block;
+};
+
+void launch_estep(const EstepArgs &a, cudaStream_t st);
+void launch_lkl_batch(const LklArgs &a, cudaStream_t st);
+// returns the grid size used (rows of loge0_part)
+unsigned freq_grid_size(const FreqArgs &a, int sm_count);
+int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st);
+void launch_reduce_loge0(const double *part, unsigned n_part, uint64_t n_ind_pad, double *out, cudaStream_t st);
+void launch_gl_ingest(const double *staged_log_gl, uint64_t n_chunk_sites, uint64_t n_ind, uint64_t first_local_site,
+                      uint64_t site_block, double *gl0, double *gl1, double *gl2, cudaStream_t st);
+void launch_viterbi(const ViterbiArgs &a, cudaStream_t st);
+void launch_geno_posterior(const double *gl0, const double *gl1, const double *gl2, const double *freq,
+                           const char *path, uint64_t n_ind, uint64_t site_block, uint64_t path_stride,
+                           uint64_t n_chunk, double *out, cudaStream_t st);
+double launch_fp64_probe(cudaStream_t st, int sm_count);
+
+}  // namespace nfh
