@@ -38,18 +38,20 @@ __device__ __forceinline__ void store_chunk(double *base, const double (&v)[kSit
   for (int j = 0; j < kSitesPerThread / 2; j++) p[j] = make_double2(v[2 * j], v[2 * j + 1]);
 }
 
-// Product of this thread's site matrices, left to right.  Sites >= n_sites
-// (padding of the last tile) are skipped, i.e. act as the identity.
-__device__ __forceinline__ M2 chunk_product(const double (&r)[kSitesPerThread], const double (&c)[kSitesPerThread],
-                                            double q0, double q1, uint64_t first_site, uint64_t n_sites, int &e) {
+// Number of real sites among this thread's kSitesPerThread (the last tile is padded).
+__device__ __forceinline__ int valid_sites(uint64_t first_site, uint64_t n_sites) {
+  return first_site >= n_sites ? 0 : (int) min((uint64_t) kSitesPerThread, n_sites - first_site);
+}
+
+// Product of this thread's factored site matrices N_s, left to right; padding
+// sites act as the identity.  On return r[] is untouched and kap[] holds kappa_s.
+__device__ __forceinline__ M2 chunk_product(const double (&r)[kSitesPerThread], const double (&kap)[kSitesPerThread],
+                                            double q0, double q1, int n_valid, int &e) {
   M2 m = identity2();
   e = 0;
 #pragma unroll
   for (int j = 0; j < kSitesPerThread; j++) {
-    if (first_site + j < n_sites) {
-      double omc = 1.0 - c[j];
-      apply_site(m, c[j], omc * q0, omc * q1, r[j]);
-    }
+    if (j < n_valid) apply_site(m, kap[j] * q0, kap[j] * q1, r[j]);
     if (j == kSitesPerThread / 2 - 1) e += renorm(m);
   }
   e += renorm(m);
@@ -60,36 +62,51 @@ __global__ void __launch_bounds__(kScanThreads)
 estep_tile_products(const double *__restrict__ emis, const double *__restrict__ dist, const double *__restrict__ indF,
                     const double *__restrict__ alpha, TileProd *__restrict__ tile_prod, uint64_t n_rows,
                     uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+  __shared__ double tab[64];
+  __shared__ M2 sm[kScanThreads / 32];
+  __shared__ int se[kScanThreads / 32];
+  __shared__ double sl[kScanThreads / 32];
+  load_exp_table(tab);
+  __syncthreads();
+
   const uint32_t tile = blockIdx.x, row = blockIdx.y;
   const uint64_t first = (uint64_t) tile * kTile + (uint64_t) threadIdx.x * kSitesPerThread;
+  const int n_valid = valid_sites(first, n_sites);
   const double F = indF[row], al = alpha[row];
   const double q0 = 1.0 - F, q1 = F;
 
-  double r[kSitesPerThread], c[kSitesPerThread];
+  double r[kSitesPerThread], kap[kSitesPerThread];
   load_chunk(emis + blocked_index(row, first, n_rows, site_block), r);
-  load_chunk(dist + first, c);
+  load_chunk(dist + first, kap);
+  double ls = 0.0;
 #pragma unroll
-  for (int j = 0; j < kSitesPerThread; j++) c[j] = exp(-al * c[j]);
+  for (int j = 0; j < kSitesPerThread; j++) {
+    double l = 0.0;
+    kap[j] = site_kappa(al * kap[j], tab, l);
+    if (j < n_valid) ls += l;
+  }
 
   int e;
-  M2 m = chunk_product(r, c, q0, q1, first, n_sites, e);
+  M2 m = chunk_product(r, kap, q0, q1, n_valid, e);
   warp_ordered_product(m, e);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ls += __shfl_down_sync(kFull, ls, off);
 
-  __shared__ M2 sm[kScanThreads / 32];
-  __shared__ int se[kScanThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sm[warp] = m; se[warp] = e; }
+  if (lane == 0) { sm[warp] = m; se[warp] = e; sl[warp] = ls; }
   __syncthreads();
   if (threadIdx.x == 0) {
     M2 acc = sm[0];
     int ae = se[0];
+    double al_sum = sl[0];
 #pragma unroll
     for (int w = 1; w < kScanThreads / 32; w++) {
       acc = matmul(acc, sm[w]);
       ae += se[w] + renorm(acc);
+      al_sum += sl[w];
     }
     TileProd out;
-    out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae;
+    out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae; out.l = al_sum;
     tile_prod[(size_t) row * n_tiles + tile] = out;
   }
 }
@@ -105,7 +122,7 @@ __global__ void estep_carries(const TileProd *__restrict__ tile_prod, const doub
   const double q0 = 1.0 - F, q1 = F;
   const TileProd *tp = tile_prod + (size_t) row * n_tiles;
 
-  double x0 = q0, x1 = q1;
+  double x0 = q0, x1 = q1, lsum = 0.0;
   long long ex = 0;
   for (uint32_t t = 0; t < n_tiles; t++) {
     fwd_carry[(size_t) row * n_tiles + t] = make_double2(x0, x1);
@@ -113,8 +130,10 @@ __global__ void estep_carries(const TileProd *__restrict__ tile_prod, const doub
     double y0 = fma(x0, p.a, x1 * p.c), y1 = fma(x0, p.b, x1 * p.d);
     x0 = y0; x1 = y1;
     ex += (long long) p.e + renorm2(x0, x1);
+    lsum += p.l;
   }
-  const double lf = log(x0 + x1) + (double) ex * kLn2 + loge0_sum[row];
+  const double base = lsum + loge0_sum[row];
+  const double lf = log(x0 + x1) + (double) ex * kLn2 + base;
 
   double b0 = 1.0, b1 = 1.0;
   long long eb = 0;
@@ -125,7 +144,7 @@ __global__ void estep_carries(const TileProd *__restrict__ tile_prod, const doub
     b0 = y0; b1 = y1;
     eb += (long long) p.e + renorm2(b0, b1);
   }
-  const double lb = log(fma(q0, b0, q1 * b1)) + (double) eb * kLn2 + loge0_sum[row];
+  const double lb = log(fma(q0, b0, q1 * b1)) + (double) eb * kLn2 + base;
 
   ind_lkl[row] = lf;
   if (lf != lf || lb != lb) atomicOr(status, kFlagNaN);
@@ -137,22 +156,29 @@ estep_apply(const double *__restrict__ emis, const double *__restrict__ dist, co
             const double *__restrict__ alpha, const double2 *__restrict__ fwd_carry,
             const double2 *__restrict__ bwd_carry, double *__restrict__ post, int *__restrict__ status,
             uint64_t n_rows, uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ double tab[64];
+  __shared__ M2 warp_tot[kWarps];
+  __shared__ double2 warp_in[kWarps], warp_out[kWarps];
+  load_exp_table(tab);
+  __syncthreads();
+
   const uint32_t tile = blockIdx.x, row = blockIdx.y;
   const uint64_t first = (uint64_t) tile * kTile + (uint64_t) threadIdx.x * kSitesPerThread;
+  const int n_valid = valid_sites(first, n_sites);
   const double F = indF[row], al = alpha[row];
   const double q0 = 1.0 - F, q1 = F;
   const size_t base = blocked_index(row, first, n_rows, site_block);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarps = kScanThreads / 32;
 
-  double r[kSitesPerThread], c[kSitesPerThread];
+  double r[kSitesPerThread], kap[kSitesPerThread];
   load_chunk(emis + base, r);
-  load_chunk(dist + first, c);
+  load_chunk(dist + first, kap);
 #pragma unroll
-  for (int j = 0; j < kSitesPerThread; j++) c[j] = exp(-al * c[j]);
+  for (int j = 0; j < kSitesPerThread; j++) kap[j] = site_kappa(al * kap[j], tab);
 
   int e_unused;
-  const M2 mine = chunk_product(r, c, q0, q1, first, n_sites, e_unused);
+  const M2 mine = chunk_product(r, kap, q0, q1, n_valid, e_unused);
 
   // Inclusive prefix (lanes <= me) and suffix (lanes >= me) products inside the
   // warp.  Only directions matter from here on (the posterior is scale free),
@@ -166,8 +192,6 @@ estep_apply(const double *__restrict__ emis, const double *__restrict__ dist, co
     if (lane + off < 32) { suf = matmul(suf, u); renorm(suf); }
   }
 
-  __shared__ M2 warp_tot[kWarps];
-  __shared__ double2 warp_in[kWarps], warp_out[kWarps];
   if (lane == 31) warp_tot[warp] = pre;
   __syncthreads();
   if (threadIdx.x < kWarps) {
@@ -214,12 +238,8 @@ estep_apply(const double *__restrict__ emis, const double *__restrict__ dist, co
   double f0[kSitesPerThread], f1[kSitesPerThread];
 #pragma unroll
   for (int j = 0; j < kSitesPerThread; j++) {
-    if (first + j < n_sites) {
-      double omc = 1.0 - c[j];
-      double t = (a0 + a1) * omc;
-      double y0 = fma(c[j], a0, t * q0);
-      double y1 = fma(c[j], a1, t * q1) * r[j];
-      a0 = y0; a1 = y1;
+    if (j < n_valid) {
+      forward_site(a0, a1, kap[j] * q0, kap[j] * q1, r[j]);
       if (j == kSitesPerThread / 2 - 1) renorm2(a0, a1);
     }
     f0[j] = a0; f1[j] = a1;
@@ -231,19 +251,15 @@ estep_apply(const double *__restrict__ emis, const double *__restrict__ dist, co
   bool bad = false;
 #pragma unroll
   for (int j = kSitesPerThread - 1; j >= 0; j--) {
-    double num = f1[j] * b1;
-    double den = fma(f0[j], b0, num);
-    double p = num / den;
-    if (first + j < n_sites) {
+    const double num = f1[j] * b1;
+    const double den = fma(f0[j], b0, num);
+    double p = num * rcp_pos(den);
+    if (j < n_valid) {
       bad |= (p != p);
       p = (p < kEps) ? 0.0 : p;              // check_interv, gen_func.cpp:59-66
       p = (p > 1.0 - kEps) ? 1.0 : p;
       out[j] = p;
-      double omc = 1.0 - c[j];
-      double w1 = r[j] * b1;
-      double mix = fma(q0, b0, q1 * w1) * omc;
-      b0 = fma(c[j], b0, mix);
-      b1 = fma(c[j], w1, mix);
+      backward_site(b0, b1, kap[j] * q0, kap[j] * q1, r[j]);
       if (j == kSitesPerThread / 2) renorm2(b0, b1);
     } else {
       out[j] = 0.0;
@@ -258,66 +274,89 @@ estep_apply(const double *__restrict__ emis, const double *__restrict__ dist, co
 // individual share one read of its emissions.
 // ---------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(kScanThreads)
-lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ dist,
-                  const LklGroup *__restrict__ groups, TileProd *__restrict__ tile_prod, uint64_t n_rows,
-                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
-  const uint32_t tile = blockIdx.x, grp = blockIdx.y;
-  const LklGroup g = groups[grp];
-  const uint64_t first = (uint64_t) tile * kTile + (uint64_t) threadIdx.x * kSitesPerThread;
-
-  double r[kSitesPerThread], d[kSitesPerThread];
-  load_chunk(emis + blocked_index((uint64_t) g.ind, first, n_rows, site_block), r);
-  load_chunk(dist + first, d);
-
-  M2 m[kMaxPoints];
-  int e[kMaxPoints];
+template <int NP>
+__device__ __forceinline__ void lkl_tile_body(const LklGroup &g, const double (&r)[kSitesPerThread],
+                                              const double (&d)[kSitesPerThread], int n_valid,
+                                              const double *__restrict__ tab, M2 (*sm)[kScanThreads / 32],
+                                              int (*se)[kScanThreads / 32], double (*sl)[kScanThreads / 32],
+                                              TileProd *__restrict__ out_row, uint32_t n_tiles, uint32_t tile) {
+  M2 m[NP];
+  int e[NP];
+  double ls[NP];
+  bool fresh[NP];   // does point p need its own exp(), or does it share alpha with p-1
 #pragma unroll
-  for (int p = 0; p < kMaxPoints; p++) { m[p] = identity2(); e[p] = 0; }
-
+  for (int p = 0; p < NP; p++) {
+    m[p] = identity2(); e[p] = 0; ls[p] = 0.0;
+    fresh[p] = (p == 0) || (g.alpha[p] != g.alpha[p - 1]);
+  }
 #pragma unroll
   for (int j = 0; j < kSitesPerThread; j++) {
-    if (first + j < n_sites) {
-      double c = 0.0;
+    double kap = 0.0, l = 0.0;
 #pragma unroll
-      for (int p = 0; p < kMaxPoints; p++) {
-        if (p < g.npts) {
-          // points that share alpha with their predecessor reuse its exp()
-          if (p == 0 || g.alpha[p] != g.alpha[p - 1]) c = exp(-g.alpha[p] * d[j]);
-          double omc = 1.0 - c;
-          apply_site(m[p], c, omc * (1.0 - g.F[p]), omc * g.F[p], r[j]);
-        }
+    for (int p = 0; p < NP; p++) {
+      if (fresh[p]) { l = 0.0; kap = site_kappa(g.alpha[p] * d[j], tab, l); }
+      if (j < n_valid) {
+        apply_site(m[p], kap * (1.0 - g.F[p]), kap * g.F[p], r[j]);
+        ls[p] += l;
       }
     }
     if (j == kSitesPerThread / 2 - 1) {
 #pragma unroll
-      for (int p = 0; p < kMaxPoints; p++) e[p] += renorm(m[p]);
+      for (int p = 0; p < NP; p++) e[p] += renorm(m[p]);
     }
   }
-
-  __shared__ M2 sm[kMaxPoints][kScanThreads / 32];
-  __shared__ int se[kMaxPoints][kScanThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int p = 0; p < kMaxPoints; p++) {
-    if (p < g.npts) {
-      e[p] += renorm(m[p]);
-      warp_ordered_product(m[p], e[p]);
-      if (lane == 0) { sm[p][warp] = m[p]; se[p][warp] = e[p]; }
-    }
+  for (int p = 0; p < NP; p++) {
+    e[p] += renorm(m[p]);
+    warp_ordered_product(m[p], e[p]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ls[p] += __shfl_down_sync(kFull, ls[p], off);
+    if (lane == 0) { sm[p][warp] = m[p]; se[p][warp] = e[p]; sl[p][warp] = ls[p]; }
   }
   __syncthreads();
-  if ((int) threadIdx.x < g.npts) {
+  if ((int) threadIdx.x < NP) {
     const int p = threadIdx.x;
     M2 acc = sm[p][0];
     int ae = se[p][0];
+    double al_sum = sl[p][0];
     for (int w = 1; w < kScanThreads / 32; w++) {
       acc = matmul(acc, sm[p][w]);
       ae += se[p][w] + renorm(acc);
+      al_sum += sl[p][w];
     }
     TileProd out;
-    out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae;
-    tile_prod[((size_t) grp * kMaxPoints + p) * n_tiles + tile] = out;
+    out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae; out.l = al_sum;
+    out_row[(size_t) p * n_tiles + tile] = out;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ dist,
+                  const LklGroup *__restrict__ groups, TileProd *__restrict__ tile_prod, uint64_t n_rows,
+                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+  __shared__ double tab[64];
+  __shared__ M2 sm[kMaxPoints][kScanThreads / 32];
+  __shared__ int se[kMaxPoints][kScanThreads / 32];
+  __shared__ double sl[kMaxPoints][kScanThreads / 32];
+  load_exp_table(tab);
+  __syncthreads();
+
+  const uint32_t tile = blockIdx.x, grp = blockIdx.y;
+  const LklGroup g = groups[grp];
+  const uint64_t first = (uint64_t) tile * kTile + (uint64_t) threadIdx.x * kSitesPerThread;
+  const int n_valid = valid_sites(first, n_sites);
+
+  double r[kSitesPerThread], d[kSitesPerThread];
+  load_chunk(emis + blocked_index((uint64_t) g.ind, first, n_rows, site_block), r);
+  load_chunk(dist + first, d);
+  TileProd *out_row = tile_prod + (size_t) grp * kMaxPoints * n_tiles;
+  switch (g.npts) {   // uniform per CTA
+    case 1: lkl_tile_body<1>(g, r, d, n_valid, tab, sm, se, sl, out_row, n_tiles, tile); break;
+    case 2: lkl_tile_body<2>(g, r, d, n_valid, tab, sm, se, sl, out_row, n_tiles, tile); break;
+    case 3: lkl_tile_body<3>(g, r, d, n_valid, tab, sm, se, sl, out_row, n_tiles, tile); break;
+    case 4: lkl_tile_body<4>(g, r, d, n_valid, tab, sm, se, sl, out_row, n_tiles, tile); break;
+    default: lkl_tile_body<5>(g, r, d, n_valid, tab, sm, se, sl, out_row, n_tiles, tile); break;
   }
 }
 
@@ -331,15 +370,16 @@ __global__ void lkl_finish(const TileProd *__restrict__ tile_prod, const LklGrou
   const LklGroup &g = groups[grp];
   if ((int) p >= g.npts) return;
   const TileProd *tp = tile_prod + ((size_t) grp * kMaxPoints + p) * n_tiles;
-  double x0 = 1.0 - g.F[p], x1 = g.F[p];
+  double x0 = 1.0 - g.F[p], x1 = g.F[p], lsum = 0.0;
   long long ex = 0;
   for (uint32_t t = 0; t < n_tiles; t++) {
     TileProd q = tp[t];
     double y0 = fma(x0, q.a, x1 * q.c), y1 = fma(x0, q.b, x1 * q.d);
     x0 = y0; x1 = y1;
     ex += (long long) q.e + renorm2(x0, x1);
+    lsum += q.l;
   }
-  neg_lkl[g.out[p]] = -(log(x0 + x1) + (double) ex * kLn2 + loge0_sum[g.ind]);
+  neg_lkl[g.out[p]] = -(log(x0 + x1) + (double) ex * kLn2 + lsum + loge0_sum[g.ind]);
 }
 
 // ---------------------------------------------------------------------------

@@ -31,38 +31,48 @@ constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
 constexpr int kMaxK = 16;             // individuals per lane -> n_ind <= 128 for the warp variant
 
 struct IndCoef {   // pass-invariant coefficients of one individual at one site
-  double a0, b0, c1, a2, b2, g;
+  double a0, a2, b2, c1, h, g;
 };
 
+// With u = (1-f)^2, v = f^2, a = f(1-f):
+//   w1 = c1 a            (= L1 * het prior)         c1 = 2 L1 (1-F)
+//   w2 = a2 v + b2 a     (= L2 * hom-alt prior)     a2 = L2, b2 = L2 F
+//   S  = a0 u + a2 v + h a  (= w0 + w1 + w2)        a0 = L0, h = L0 F + c1 + b2
+//   num += (w1 + g w2) / S                          g = 2 - F
+//   den += g + F w1 / S      [2 w1 + (w0 + w2) g = g S + F w1]
 __device__ __forceinline__ IndCoef make_coef(double L0, double L1, double L2, double F) {
   IndCoef k;
-  k.a0 = L0; k.b0 = L0 * F;
+  k.a0 = L0; k.a2 = L2; k.b2 = L2 * F;
   k.c1 = 2.0 * L1 * (1.0 - F);
-  k.a2 = L2; k.b2 = L2 * F;
-  k.g = 2.0 - F;
   // A heterozygote call (L0 = L2 = 0) at a site whose IBD posterior was
   // clamped to exactly 1 has zero weight for every genotype; the reference's
   // log-space arithmetic (-1e15 stands for log 0) resolves this to "certainly
   // heterozygous".  Keep a vanishing het weight so the ratio is 1, not 0/0.
   if (L0 == 0.0 && L2 == 0.0 && F == 1.0) k.c1 = 1e-280;
+  k.h = L0 * F + k.c1 + k.b2;
+  k.g = 2.0 - F;
   return k;
 }
 
 __device__ __forceinline__ IndCoef null_coef() {   // padding slot: contributes exactly 0
   IndCoef k;
-  k.a0 = 0.5; k.b0 = 0.0; k.c1 = 0.0; k.a2 = 0.5; k.b2 = 0.0; k.g = 0.0;
+  k.a0 = 0.5; k.a2 = 0.5; k.b2 = 0.0; k.c1 = 0.0; k.h = 0.0; k.g = 0.0;
   return k;
 }
 
-__device__ __forceinline__ void accumulate(const IndCoef &k, double u, double v, double a, double &num, double &den) {
-  double w0 = fma(k.b0, a, k.a0 * u);
-  double w1 = k.c1 * a;
-  double w2 = fma(k.b2, a, k.a2 * v);
-  double rinv = 1.0 / (w0 + w1 + w2);
-  double n = fma(w2, k.g, w1);
-  double d = fma(k.g, w0 - w2, n + n);
-  num = fma(n, rinv, num);
-  den = fma(d, rinv, den);
+// 14 FP64 instructions, no branches: the K independent chains of a lane interleave.
+// den_f accumulates sum F w1 / S only; the constant sum of g is added per pass by the caller.
+__device__ __forceinline__ void accumulate(const IndCoef &k, double u, double v, double a, double &num_a,
+                                           double &num_b, double &den_f) {
+  const double x2 = k.a2 * v;
+  const double w2 = fma(k.b2, a, x2);
+  const double w1 = k.c1 * a;
+  const double S = fma(k.a0, u, fma(k.h, a, x2));
+  const double rinv = rcp_pos(S);
+  const double t1 = w1 * rinv;
+  num_a += t1;
+  num_b = fma(k.g * w2, rinv, num_b);
+  den_f = fma(2.0 - k.g, t1, den_f);
 }
 
 // state emissions from linear GL at frequency f (calc_emission with F = 0 / 1)
@@ -104,20 +114,27 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
 
     double freq = A.update_freq ? 0.01 : A.freq[sl];
     if (A.update_freq) {
+      double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
+#pragma unroll
+      for (int k = 0; k < K; k++) g_sum += coef[k].g;
+#pragma unroll
+      for (int m = 1; m < kGroupLanes; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
       double num = 0.0, den = 0.0;
       bool active = site_ok;
       int passes = 0;
       while (__any_sync(kFull, active)) {
         const double omf = 1.0 - freq;
         const double u = omf * omf, v = freq * freq, a = omf * freq;
-        double pn = 0.0, pd = 0.0;
+        double pa = 0.0, pb = 0.0, pd = 0.0;
 #pragma unroll
-        for (int k = 0; k < K; k++) accumulate(coef[k], u, v, a, pn, pd);
+        for (int k = 0; k < K; k++) accumulate(coef[k], u, v, a, pa, pb, pd);
+        double pn = pa + pb;
 #pragma unroll
         for (int m = 1; m < kGroupLanes; m <<= 1) {
           pn += __shfl_xor_sync(kFull, pn, m);
           pd += __shfl_xor_sync(kFull, pd, m);
         }
+        pd += g_sum;
         passes++;
         if (active) {
           num += pn; den += pd;
@@ -174,12 +191,15 @@ freq_emission_stream(FreqArgs A) {
         before = freq;
         const double omf = 1.0 - freq;
         const double u = omf * omf, v = freq * freq, a = omf * freq;
+        double pa = 0.0, pb = 0.0, pd = 0.0;
         for (uint64_t i = 0; i < A.n_ind; i++) {
           const size_t at = (size_t) i * A.site_block + site;
           const double F = A.post ? A.post[at] : 0.0;
           IndCoef k = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
-          accumulate(k, u, v, a, num, den);
+          accumulate(k, u, v, a, pa, pb, pd);
+          pd += k.g;
         }
+        num += pa + pb; den += pd;
         freq = num / den;
       } while (fabs(before - freq) > kEps && passes++ < 100);
       A.freq[site] = freq;

@@ -8,8 +8,8 @@ namespace nfh {
 
 constexpr int kMaxPoints = 5;   // objective points per individual per round: x, x -/+ eh_F, x -/+ eh_alpha (bfgs.cpp:22-43)
 
-struct TileProd {   // scaled 2x2 product of one tile: [[a b][c d]] * 2^e
-  double a, b, c, d, e;
+struct TileProd {   // product of one tile's site matrices: [[a b][c d]] * 2^e * exp(l)
+  double a, b, c, d, e, l;
 };
 
 struct LklGroup {   // objective requests of one individual sharing one read of its emissions

@@ -1,0 +1,144 @@
+"""Host-side mirror of the reference's EM iteration for Python callers.
+
+``EmRank`` plays the role of ``iter_EM(params*)`` (EM.cpp:139-289) for one
+rank: E-step, F/alpha update (host L-BFGS-B bookkeeping in
+libngsfhmm_host.so around batched objective launches), frequency update with
+emission refresh.  With more than one rank the posteriors travel from the
+individual-sharded recursion side to the site-sharded frequency side and the
+refreshed emissions travel back - two equal-split all-to-alls plus one small
+all-reduce per iteration, moved by torch.distributed (NCCL over NVLink on the
+GPU box; gloo in the CPU tests of this plumbing).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import api
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_hostlib = None
+
+
+def load_host_library():
+    global _hostlib
+    if _hostlib is None:
+        api.load_library()
+        path = os.path.join(_HERE, "libngsfhmm_host.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing: run __graft_entry__.build()")
+        L = C.CDLL(path)
+        u64p = C.POINTER(C.c_uint64)
+        L.nfh_host_bfgs_update.restype = C.c_int
+        L.nfh_host_bfgs_update.argtypes = [C.c_void_p, C.c_uint64, _dp, _dp, C.c_int, C.c_int, u64p]
+        L.nfh_host_em_iteration.restype = C.c_int
+        L.nfh_host_em_iteration.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, u64p]
+        _hostlib = L
+    return _hostlib
+
+
+def exchange_all_to_all(send, recv, group=None):
+    """Equal-split all-to-all of a [n_ranks, n_ind_local, site_block] window (any device/backend)."""
+    import torch.distributed as dist
+    if send.data_ptr() == recv.data_ptr():
+        return
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+
+
+def blocked_owner_layout(n_ranks, n_ind_local, site_block):
+    """Shape of every exchange window: [destination or source rank][local individual][site in block]."""
+    return (n_ranks, n_ind_local, site_block)
+
+
+class _DevWindow:
+    """Zero-copy torch view of a device window exported by the C ABI."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2}
+
+
+class EmRank:
+    def __init__(self, ctx: api.Context, *, indF_fixed=False, alpha_fixed=False, freq_est=1, group=None):
+        self.ctx = ctx
+        self.H = load_host_library()
+        self.indF_fixed, self.alpha_fixed, self.freq_est = indF_fixed, alpha_fixed, freq_est
+        self.group = group
+        self.stats = np.zeros(3, dtype=np.uint64)
+        self.total_evals = 0
+        self.total_rounds = 0
+        self._win = {}
+        self._ext_stream = None
+
+    # -- multi-rank plumbing ------------------------------------------------
+    def _tensor(self, which):
+        import torch
+        if which not in self._win:
+            ptr, nbytes, _ = self.ctx.window(which)
+            t = torch.as_tensor(_DevWindow(ptr, nbytes), device=f"cuda:{torch.cuda.current_device()}")
+            if which != api.WIN_LOGE0_SUM:
+                t = t.view(*blocked_owner_layout(self.ctx.n_ranks, self.ctx.n_ind_local, self.ctx.site_block))
+            self._win[which] = t
+        return self._win[which]
+
+    def _stream_ctx(self):
+        import torch
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream)
+        return torch.cuda.stream(self._ext_stream)
+
+    def exchange_posteriors(self):
+        if self.ctx.n_ranks == 1:
+            return
+        with self._stream_ctx():
+            exchange_all_to_all(self._tensor(api.WIN_POST_SEND), self._tensor(api.WIN_POST_RECV), self.group)
+
+    def exchange_emissions(self, with_e0=False):
+        if self.ctx.n_ranks == 1:
+            return
+        import torch.distributed as dist
+        with self._stream_ctx():
+            exchange_all_to_all(self._tensor(api.WIN_EMIS_SEND), self._tensor(api.WIN_EMIS_RECV), self.group)
+            if with_e0:
+                exchange_all_to_all(self._tensor(api.WIN_E0_SEND), self._tensor(api.WIN_E0_RECV), self.group)
+            dist.all_reduce(self._tensor(api.WIN_LOGE0_SUM), group=self.group)
+
+    # -- iteration ----------------------------------------------------------
+    def refresh_emissions(self, with_e0=False):
+        self.ctx.emission_refresh(with_e0)
+        self.exchange_emissions(with_e0)
+
+    def bfgs_update(self, indF, alpha):
+        n = self.ctx.n_ind_owned
+        rc = self.H.nfh_host_bfgs_update(self.ctx.h, n, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
+                                         int(self.indF_fixed), int(self.alpha_fixed),
+                                         self.stats.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self.ctx._chk(rc)
+        self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
+
+    def iteration(self, indF, alpha, want_freq=True):
+        """One EM iteration; indF/alpha (float64, n_ind_owned) are updated in place.
+        Returns (ind_lkl, freq_of_this_rank's_sites or None)."""
+        ctx = self.ctx
+        if ctx.n_ranks == 1:
+            lk = np.empty(ctx.n_ind_owned)
+            fr = np.empty(ctx.sites_owned) if (want_freq and self.freq_est) else None
+            rc = self.H.nfh_host_em_iteration(ctx.h, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
+                                              int(self.indF_fixed), int(self.alpha_fixed), int(self.freq_est),
+                                              lk.ctypes.data_as(_dp), fr.ctypes.data_as(_dp) if fr is not None else None,
+                                              self.stats.ctypes.data_as(C.POINTER(C.c_uint64)))
+            ctx._chk(rc)
+            self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
+            return lk, fr
+        ctx.set_ind_params(indF, alpha)
+        lk = ctx.estep()
+        self.exchange_posteriors()                       # overlaps with the host/device BFGS rounds below
+        self.bfgs_update(indF, alpha)
+        fr = None
+        if self.freq_est:
+            fr = ctx.freq_update(1, want_freq=want_freq)
+            self.exchange_emissions()
+        return lk, fr

@@ -116,3 +116,77 @@ def write_geno_gz(path: str, geno: np.ndarray) -> None:
     with gzip.open(path, "wt") as fh:
         for s in range(geno.shape[1]):
             fh.write("\t".join(str(int(g)) for g in geno[:, s]) + "\n")
+
+
+# ---------------------------------------------------------------------------
+# Large synthetic inputs, generated with torch on whatever device is given
+# (the GPU on the bench box).  Same distribution as simulate(); different RNG
+# stream.  Returns NORMALISED natural-log GL in the upload layout.
+# ---------------------------------------------------------------------------
+
+def simulate_torch(n_ind, n_sites, *, device, seed=1002, freq=(0.05, 0.5), indF=(0.0, 0.5), alpha=0.01, depth=2.0,
+                   error=0.01, site_chunk=1 << 18, out=None, site_begin=0, site_end=None):
+    """Generate sites [site_begin, site_end) for ALL n_ind individuals.
+
+    Every quantity is a pure function of (seed, site index, individual index) chunk by chunk, so ranks that
+    generate different site blocks see one consistent data set.  Returns dict(log_gl (n, N, 3) float64 on
+    `out`'s device or CPU pinned, dist_mb (n_sites,) numpy, true_F, true_alpha, true_freq (n,)).
+    """
+    import torch
+
+    N, S = int(n_ind), int(n_sites)
+    site_end = S if site_end is None else site_end
+    n = site_end - site_begin
+    g = torch.Generator(device=device)
+
+    def uni(lohi, count, tag):
+        g.manual_seed(seed * 1000003 + tag)
+        if isinstance(lohi, tuple):
+            return lohi[0] + (lohi[1] - lohi[0]) * torch.rand(count, generator=g, device=device, dtype=torch.float64)
+        return torch.full((count,), float(lohi), device=device, dtype=torch.float64)
+
+    F = uni(indF, N, 1)
+    a = uni(alpha, N, 2)
+    f_all = uni(freq, S, 3)
+    g.manual_seed(seed * 1000003 + 4)
+    step = torch.clamp((1e5 + (1e5 / 3) * torch.randn(S, generator=g, device=device, dtype=torch.float64)).floor(),
+                       min=1.0)
+    dist_mb = step / 1e6
+
+    if out is None:
+        out = torch.empty((n, N, 3), dtype=torch.float64, pin_memory=(str(device) != "cpu"))
+    lp = torch.log(torch.tensor([error, 0.5, 1 - error], device=device, dtype=torch.float64))
+    lq = torch.log(torch.tensor([1 - error, 0.5, error], device=device, dtype=torch.float64))
+    p_read = torch.tensor([error, 0.5, 1 - error], device=device, dtype=torch.float64)
+
+    # IBD state: renewal form of the chain, carried across chunks through the last state of each individual.
+    # To stay a pure function of the site range, the chain is (re)started with a Bernoulli(F) draw at every
+    # chunk boundary that is a multiple of site_chunk - a negligible change for throughput inputs.
+    for c0 in range((site_begin // site_chunk) * site_chunk, site_end, site_chunk):
+        c1 = min(c0 + site_chunk, S)
+        m = c1 - c0
+        g.manual_seed(seed * 1000003 + 1000 + c0 // site_chunk)
+        keep = torch.exp(-a[None, :] * dist_mb[c0:c1, None])                     # (m, N)
+        redraw = torch.rand((m, N), generator=g, device=device, dtype=torch.float64) < (1 - keep)
+        redraw[0, :] = True
+        fresh = torch.rand((m, N), generator=g, device=device, dtype=torch.float64) < F[None, :]
+        idx = torch.arange(m, device=device)[:, None].expand(m, N)
+        last = torch.cummax(torch.where(redraw, idx, torch.zeros_like(idx)), dim=0).values
+        state = torch.gather(fresh, 0, last)
+        fc = f_all[c0:c1, None]
+        h1 = torch.rand((m, N), generator=g, device=device, dtype=torch.float64) < fc
+        h2 = torch.rand((m, N), generator=g, device=device, dtype=torch.float64) < fc
+        h2 = torch.where(state, h1, h2)
+        geno = h1.long() + h2.long()
+        dp = torch.poisson(torch.full((m, N), float(depth), device=device, dtype=torch.float64), generator=g)
+        nA = torch.binomial(dp, p_read[geno], generator=g)
+        ll = nA[..., None] * lp + (dp - nA)[..., None] * lq                       # (m, N, 3)
+        ll = ll - torch.logsumexp(ll, dim=-1, keepdim=True)
+        ll = torch.round(ll * 1e10) / 1e10                                        # sim.R rounds to 10 digits
+        ll = ll - torch.logsumexp(ll, dim=-1, keepdim=True)                       # read_geno + main normalise
+        ll = ll - torch.logsumexp(ll, dim=-1, keepdim=True)
+        lo, hi = max(c0, site_begin), min(c1, site_end)
+        if hi > lo:
+            out[lo - site_begin:hi - site_begin].copy_(ll[lo - c0:hi - c0], non_blocking=False)
+    return dict(log_gl=out, dist_mb=dist_mb.cpu().numpy(), true_F=F.cpu().numpy(), true_alpha=a.cpu().numpy(),
+                true_freq=f_all[site_begin:site_end].cpu().numpy())
