@@ -14,12 +14,18 @@
 #include <stdint.h>
 
 #include "nfh_math.cuh"
+#include "nfh_tma.cuh"
 
 namespace nfh {
 
-constexpr int kSitesPerThread = 8;                       // contiguous sites owned by one thread
-constexpr int kScanThreads = 256;                        // threads per CTA in the scan kernels
-constexpr int kTile = kSitesPerThread * kScanThreads;    // 2048 sites per CTA tile
+// Site tiling of the scan kernels.  Every thread owns kChunk CONSECUTIVE sites;
+// kChunk is odd so that thread t reading element t*kChunk + j of a tile staged
+// densely in shared memory is bank-conflict free (stride 33 doubles).
+constexpr int kChunk = 33;                               // sites per thread
+constexpr int kSub = 11;                                 // sub-block of a chunk held in registers (kChunk = 3 kSub)
+constexpr int kScanThreads = 128;                        // threads per CTA in the scan kernels
+constexpr int kTile = kChunk * kScanThreads;             // 4224 sites per CTA tile
+constexpr uint32_t kTileBytes = kTile * sizeof(double);  // 33792, a multiple of 16 (TMA bulk copy)
 constexpr double kLn2 = 0.693147180559945309417232121458;
 constexpr double kEps = 1e-5;                            // EPSILON, gen_func.hpp:16
 constexpr unsigned kFull = 0xffffffffu;
@@ -75,15 +81,17 @@ __device__ __forceinline__ int renorm2(double &x, double &y) {
 // The scalar c only shifts the log-likelihood by -alpha d and cancels in the
 // posterior and in every arg-max, so the recursions multiply by N_s (4 FMA +
 // 2 MUL + 2 ADD per 2x2 update instead of 15 operations) and the scalars are
-// summed separately (SiteScale::log_scale).
+// summed separately (the log_scale argument of site_kappa).
 //
 // Chromosome starts have d = +inf (c = 0, T_s = 1 q').  They, and any site with
-// alpha d > 138, use kappa = 2^200 and the scalar 2^-200: the neglected term
-// I/kappa is below 2^-199 relative, far under double rounding.
+// alpha d > 76, use kappa = 2^110 and the scalar 2^-110.  The neglected term
+// I/kappa must vanish against kappa q_l for the smallest q_l the optimiser can
+// reach (1e-15 ~ 2^-50, EM.cpp:425-426): 2^-110 / 2^-50 = 2^-60, below half an
+// ulp.  Growth is bounded by renormalising at least every 6 sites (2^660).
 // ---------------------------------------------------------------------------
-constexpr double kBigX = 138.0;                       // e^138 < 2^200
-constexpr double kBigKappa = 1.6069380442589903e60;   // 2^200
-constexpr double kBigLogScale = 138.62943611198907;   // 200 ln 2
+constexpr double kBigX = 76.0;                        // e^76 < 2^110
+constexpr double kBigKappa = 1.2980742146337069e33;   // 2^110
+constexpr double kBigLogScale = 76.24618986159398;    // 110 ln 2
 
 // kappa for x = alpha * d; adds log c (natural log) to log_scale.
 __device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab, double &log_scale) {

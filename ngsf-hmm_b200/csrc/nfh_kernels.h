@@ -12,6 +12,10 @@ struct TileProd {   // product of one tile's site matrices: [[a b][c d]] * 2^e *
   double a, b, c, d, e, l;
 };
 
+struct ChunkProd {   // product of one thread's 33 site matrices, same encoding as TileProd
+  double a, b, c, d, e, l;
+};
+
 struct LklGroup {   // objective requests of one individual sharing one read of its emissions
   int ind;
   int npts;
@@ -25,8 +29,8 @@ struct EstepArgs {
   const double *dist;        // [n_ranks * site_block] Mb
   const double *indF, *alpha;
   const double *loge0_sum;   // [n_rows] sum over sites of log e0
-  TileProd *tile_prod;       // [n_rows][n_tiles]
-  double2 *fwd_carry, *bwd_carry;
+  ChunkProd *chunk_prod;     // [n_rows][n_tiles * 128]
+  double2 *fwd_carry, *bwd_carry;   // per chunk
   double *post;              // blocked like emis
   double *ind_lkl;
   int *status;
