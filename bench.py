@@ -38,7 +38,7 @@ N_SITES = 1_000_000
 START_FREQ, START_F, START_ALPHA = 0.1, 0.1, 0.2
 # algorithmic work per unit, stated in DESIGN.md "Measurement"
 ESTEP_BYTES_PER_IND_SITE = 24.0          # read 2 emissions, write 1 posterior
-FREQ_FLOPS_PER_IND_PASS = 30.0           # linear-space est_maf contribution, reciprocal counted as its 5-DFMA sequence
+FREQ_FLOPS_PER_IND_PASS = 15.0           # linear-space est_maf contribution: 9 FP64 instructions (6 of them FMA)
 FREQ_PASSES = 101.0                      # upper bound per site (gen_func.cpp:1006); ~90% of sites hit it
 LKL_FLOPS_PER_IND_SITE_POINT = 24.0      # 2x2 product update (12 flop-slots, 6 of them FMA) per objective point
 EXP_FLOPS = 32.0                         # one FP64 exp() = 14 DFMA + 2 DADD + range handling

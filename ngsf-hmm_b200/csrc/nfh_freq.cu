@@ -19,60 +19,62 @@
 //   w0 = L0 (u + a F)   w1 = L1 2a(1-F)   w2 = L2 (v + a F)     (HWE prior x GL)
 //   num += (w1 + w2 (2-F)) / (w0+w1+w2)
 //   den += (2 w1 + (w0+w2)(2-F)) / (w0+w1+w2)
+#include <cstdlib>
+
 #include "nfh_device.cuh"
 #include "nfh_kernels.h"
 
 namespace nfh {
 
-constexpr int kGroupLanes = 8;        // lanes sharing one site (individual groups) in the warp variant
 constexpr int kFreqThreads = 128;
-constexpr int kSitesPerWarp = 32 / kGroupLanes;
-constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
-constexpr int kMaxK = 16;             // individuals per lane -> n_ind <= 128 for the warp variant
+constexpr int kMaxK = 16;             // most individuals one lane keeps in registers
 
 struct IndCoef {   // pass-invariant coefficients of one individual at one site
-  double a0, a2, b2, c1, h, g;
+  double a0, a2, h;      // S = a0 u + a2 v + h a          (sum of the three genotype weights)
+  double na, nv, da;     // numerator weights: (na a + nv v) / S ; F-weighted het term: da a / S
+  double g;              // 2 - F (only summed once per site, not used per pass)
 };
 
-// With u = (1-f)^2, v = f^2, a = f(1-f):
-//   w1 = c1 a            (= L1 * het prior)         c1 = 2 L1 (1-F)
-//   w2 = a2 v + b2 a     (= L2 * hom-alt prior)     a2 = L2, b2 = L2 F
-//   S  = a0 u + a2 v + h a  (= w0 + w1 + w2)        a0 = L0, h = L0 F + c1 + b2
-//   num += (w1 + g w2) / S                          g = 2 - F
-//   den += g + F w1 / S      [2 w1 + (w0 + w2) g = g S + F w1]
+// With u = (1-f)^2, v = f^2, a = f(1-f), GL (L0,L1,L2), IBD posterior F, g = 2 - F:
+//   w0 = L0 (u + a F)   w1 = 2 L1 (1-F) a   w2 = L2 (v + a F)           (HWE prior x GL)
+//   S  = w0 + w1 + w2 = L0 u + L2 v + (L0 F + 2 L1 (1-F) + L2 F) a
+//   num += (w1 + g w2) / S      = [ (2 L1 (1-F) + g L2 F) a + g L2 v ] / S
+//   den += (2 w1 + (w0+w2) g)/S = g + F w1 / S  = g + [ 2 L1 (1-F) F a ] / S
+// so per pass and individual only S, 1/S and three FMAs into
+//   A1 = sum na/S,  A2 = sum nv/S,  A3 = sum da/S
+// are needed (9 FP64 instructions); num = a A1 + v A2 and den = sum g + a A3
+// are formed once per pass.
 __device__ __forceinline__ IndCoef make_coef(double L0, double L1, double L2, double F) {
   IndCoef k;
-  k.a0 = L0; k.a2 = L2; k.b2 = L2 * F;
-  k.c1 = 2.0 * L1 * (1.0 - F);
+  double c1 = 2.0 * L1 * (1.0 - F);
   // A heterozygote call (L0 = L2 = 0) at a site whose IBD posterior was
   // clamped to exactly 1 has zero weight for every genotype; the reference's
   // log-space arithmetic (-1e15 stands for log 0) resolves this to "certainly
   // heterozygous".  Keep a vanishing het weight so the ratio is 1, not 0/0.
-  if (L0 == 0.0 && L2 == 0.0 && F == 1.0) k.c1 = 1e-280;
-  k.h = L0 * F + k.c1 + k.b2;
+  if (L0 == 0.0 && L2 == 0.0 && F == 1.0) c1 = 1e-280;
   k.g = 2.0 - F;
+  k.a0 = L0; k.a2 = L2;
+  k.h = L0 * F + c1 + L2 * F;
+  k.na = c1 + k.g * (L2 * F);
+  k.nv = k.g * L2;
+  k.da = c1 * F;
   return k;
 }
 
 __device__ __forceinline__ IndCoef null_coef() {   // padding slot: contributes exactly 0
   IndCoef k;
-  k.a0 = 0.5; k.a2 = 0.5; k.b2 = 0.0; k.c1 = 0.0; k.h = 0.0; k.g = 0.0;
+  k.a0 = 0.5; k.a2 = 0.5; k.h = 0.0; k.na = 0.0; k.nv = 0.0; k.da = 0.0; k.g = 0.0;
   return k;
 }
 
-// 14 FP64 instructions, no branches: the K independent chains of a lane interleave.
-// den_f accumulates sum F w1 / S only; the constant sum of g is added per pass by the caller.
-__device__ __forceinline__ void accumulate(const IndCoef &k, double u, double v, double a, double &num_a,
-                                           double &num_b, double &den_f) {
-  const double x2 = k.a2 * v;
-  const double w2 = fma(k.b2, a, x2);
-  const double w1 = k.c1 * a;
-  const double S = fma(k.a0, u, fma(k.h, a, x2));
+// 9 FP64 instructions + 1 MUFU, no branches.
+__device__ __forceinline__ void accumulate(const IndCoef &k, double u, double v, double a, double &A1, double &A2,
+                                           double &A3) {
+  const double S = fma(k.a0, u, fma(k.a2, v, k.h * a));
   const double rinv = rcp_pos(S);
-  const double t1 = w1 * rinv;
-  num_a += t1;
-  num_b = fma(k.g * w2, rinv, num_b);
-  den_f = fma(2.0 - k.g, t1, den_f);
+  A1 = fma(k.na, rinv, A1);
+  A2 = fma(k.nv, rinv, A2);
+  A3 = fma(k.da, rinv, A3);
 }
 
 // state emissions from linear GL at frequency f (calc_emission with F = 0 / 1)
@@ -84,11 +86,14 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
   e1 = fma(L0, u + a, L2 * (v + a));       // het prior is exp(-1e15) = 0 when F == 1
 }
 
-template <int K>
+// G lanes share one site (G divides 32); each lane keeps K individuals.
+template <int G, int K>
 __global__ void __launch_bounds__(kFreqThreads)
 freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
+  constexpr int kSitesPerWarp = 32 / G;
+  constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane & (kGroupLanes - 1), sub = lane / kGroupLanes;
+  const int grp = lane & (G - 1), sub = lane / G;
   extern __shared__ double loge0_acc[];     // [warps][n_ind_pad]
   for (unsigned i = threadIdx.x; i < (kFreqThreads / 32) * A.n_ind_pad; i += kFreqThreads) loge0_acc[i] = 0.0;
   __syncthreads();
@@ -99,38 +104,68 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
 
-    IndCoef coef[K];
+    double a0[K], a2[K], hh[K], na[K], nv[K], da[K];
+    double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const uint64_t i = (uint64_t) grp + (uint64_t) kGroupLanes * k;
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      IndCoef c;
       if (i < A.n_ind) {
         const size_t at = (size_t) i * A.site_block + sl;
         const double F = A.post ? A.post[at] : 0.0;
-        coef[k] = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
+        c = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
       } else {
-        coef[k] = null_coef();
+        c = null_coef();
       }
+      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; da[k] = c.da;
+      g_sum += c.g;
     }
 
     double freq = A.update_freq ? 0.01 : A.freq[sl];
     if (A.update_freq) {
-      double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
 #pragma unroll
-      for (int k = 0; k < K; k++) g_sum += coef[k].g;
-#pragma unroll
-      for (int m = 1; m < kGroupLanes; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
+      for (int m = 1; m < G; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
       double num = 0.0, den = 0.0;
       bool active = site_ok;
       int passes = 0;
       while (__any_sync(kFull, active)) {
         const double omf = 1.0 - freq;
         const double u = omf * omf, v = freq * freq, a = omf * freq;
-        double pa = 0.0, pb = 0.0, pd = 0.0;
+        double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;   // two interleaved accumulator sets
+        // Stage-major over batches of individuals: the warp scheduler issues in
+        // order, so the independent chains are laid out side by side - every
+        // dependent pair of FP64 instructions is a whole batch apart (DFMA
+        // latency is ~8.4 cycles at one issue per 2 cycles per sub-partition).
+        constexpr int kBatch = K <= 8 ? K : (K + 1) / 2;
 #pragma unroll
-        for (int k = 0; k < K; k++) accumulate(coef[k], u, v, a, pa, pb, pd);
-        double pn = pa + pb;
+        for (int k0 = 0; k0 < K; k0 += kBatch) {
+          double S[kBatch], y[kBatch], e[kBatch];
 #pragma unroll
-        for (int m = 1; m < kGroupLanes; m <<= 1) {
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) S[b] = hh[k0 + b] * a;
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) S[b] = fma(a2[k0 + b], v, S[b]);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) S[b] = fma(a0[k0 + b], u, S[b]);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) y[b] = rcp_seed(S[b]);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) e[b] = fma(-S[b], y[b], 1.0);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) e[b] = fma(e[b], e[b], e[b]);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) if (k0 + b < K) y[b] = fma(y[b], e[b], y[b]);
+#pragma unroll
+          for (int b = 0; b < kBatch; b++) {
+            if (k0 + b < K) {
+              if (b & 1) { B1 = fma(na[k0 + b], y[b], B1); B2 = fma(nv[k0 + b], y[b], B2); B3 = fma(da[k0 + b], y[b], B3); }
+              else       { A1 = fma(na[k0 + b], y[b], A1); A2 = fma(nv[k0 + b], y[b], A2); A3 = fma(da[k0 + b], y[b], A3); }
+            }
+          }
+        }
+        double pn = fma(a, A1 + B1, v * (A2 + B2));
+        double pd = a * (A3 + B3);
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
           pn += __shfl_xor_sync(kFull, pn, m);
           pd += __shfl_xor_sync(kFull, pd, m);
         }
@@ -139,7 +174,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
         if (active) {
           num += pn; den += pd;
           const double before = freq;
-          freq = num / den;
+          freq = num * rcp_pos<true>(den);
           // do { ... } while (|before - freq| > EPSILON && iters++ < 100)   gen_func.cpp:1006
           active = (fabs(before - freq) > kEps) && (passes <= 100);
         }
@@ -147,23 +182,22 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       if (site_ok && grp == 0) A.freq[site] = freq;
     }
 
-    // emission refresh from the same site (L1 is re-read: the coefficients
-    // hold 2 L1 (1-F), which loses L1 when F == 1)
+    // emission refresh from the same site (L1 is re-read: the coefficients fold it with F)
 #pragma unroll
     for (int k = 0; k < K; k++) {
-      const uint64_t i = (uint64_t) grp + (uint64_t) kGroupLanes * k;
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
       double le0 = 0.0;
       if (i < A.n_ind && site_ok) {
         const size_t at = (size_t) i * A.site_block + site;
         double e0, e1;
-        emissions(coef[k].a0, A.gl1[at], coef[k].a2, freq, e0, e1);
+        emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
         A.emis[at] = e1 / e0;
         if (A.e0) A.e0[at] = e0;
         le0 = log(e0);
       }
       // sum over the warp's sites (lanes with equal grp), fixed order
 #pragma unroll
-      for (int m = kGroupLanes; m < 32; m <<= 1) le0 += __shfl_xor_sync(kFull, le0, m);
+      for (int m = G; m < 32; m <<= 1) le0 += __shfl_xor_sync(kFull, le0, m);
       if (sub == 0 && i < A.n_ind_pad) my_acc[i] += le0;
     }
   }
@@ -191,15 +225,15 @@ freq_emission_stream(FreqArgs A) {
         before = freq;
         const double omf = 1.0 - freq;
         const double u = omf * omf, v = freq * freq, a = omf * freq;
-        double pa = 0.0, pb = 0.0, pd = 0.0;
+        double A1 = 0.0, A2 = 0.0, A3 = 0.0, gs = 0.0;
         for (uint64_t i = 0; i < A.n_ind; i++) {
           const size_t at = (size_t) i * A.site_block + site;
           const double F = A.post ? A.post[at] : 0.0;
           IndCoef k = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
-          accumulate(k, u, v, a, pa, pb, pd);
-          pd += k.g;
+          accumulate(k, u, v, a, A1, A2, A3);
+          gs += k.g;
         }
-        num += pa + pb; den += pd;
+        num += fma(a, A1, v * A2); den += fma(a, A3, gs);
         freq = num / den;
       } while (fabs(before - freq) > kEps && passes++ < 100);
       A.freq[site] = freq;
@@ -307,33 +341,68 @@ __global__ void __launch_bounds__(256) fp64_probe(double *sink, int iters) {
 
 // ---------------------------------------------------------------------------
 
+// Choose lanes-per-site G and individuals-per-lane K <= 16: the fewest padded
+// slots wins (measured at 100 individuals: G=8,K=13 12.6 ms vs G=16,K=7 13.7 ms
+// per million sites - padding costs more than the extra occupancy gains).
+static bool pick_shape(uint64_t n_ind, int &G, int &K) {
+  if (const char *force = getenv("NFH_FREQ_G")) {   // tuning override: lanes per site
+    const int g = atoi(force);
+    const int k = (int) ((n_ind + g - 1) / g);
+    if ((g == 4 || g == 8 || g == 16 || g == 32) && k >= 1 && k <= kMaxK) { G = g; K = k; return true; }
+  }
+  int best_g = 0, best_k = 0;
+  uint64_t best_slots = ~0ull;
+  for (int g = 4; g <= 32; g <<= 1) {
+    const int k = (int) ((n_ind + g - 1) / g);
+    if (k < 1 || k > kMaxK) continue;
+    const uint64_t slots = (uint64_t) g * k;
+    if (slots <= best_slots) { best_slots = slots; best_g = g; best_k = k; }
+  }
+  G = best_g; K = best_k;
+  return best_g != 0;
+}
+
 unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
-  if (a.n_ind <= (uint64_t) kGroupLanes * kMaxK) {
-    unsigned tiles = (unsigned) ((a.sites_owned + kSitesPerCta - 1) / kSitesPerCta);
+  int G, K;
+  if (pick_shape(a.n_ind, G, K)) {
+    const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
+    unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
     unsigned cap = (unsigned) sm_count * 4u;
     return tiles < cap ? (tiles ? tiles : 1u) : cap;
   }
   return 64;   // chunks of loge0_rowsum
 }
 
-template <int K>
-static void launch_warp_variant(const FreqArgs &a, unsigned grid, unsigned tiles, cudaStream_t st) {
+template <int G, int K>
+static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
+  const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   size_t smem = (size_t) (kFreqThreads / 32) * a.n_ind_pad * sizeof(double);
-  freq_emission_warp<K><<<grid, kFreqThreads, smem, st>>>(a, tiles);
+  freq_emission_warp<G, K><<<grid, kFreqThreads, smem, st>>>(a, tiles);
+}
+
+template <int G>
+static bool dispatch_k(int K, const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  switch (K) {
+#define NFH_CASE(k) case k: launch_warp_variant<G, k>(a, grid, st); return true;
+    NFH_CASE(1) NFH_CASE(2) NFH_CASE(3) NFH_CASE(4) NFH_CASE(5) NFH_CASE(6) NFH_CASE(7) NFH_CASE(8)
+    NFH_CASE(9) NFH_CASE(10) NFH_CASE(11) NFH_CASE(12) NFH_CASE(13) NFH_CASE(14) NFH_CASE(15) NFH_CASE(16)
+#undef NFH_CASE
+    default: return false;
+  }
 }
 
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  if (a.n_ind <= (uint64_t) kGroupLanes * kMaxK) {
-    const unsigned tiles = (unsigned) ((a.sites_owned + kSitesPerCta - 1) / kSitesPerCta);
-    const int K = (int) ((a.n_ind + kGroupLanes - 1) / kGroupLanes);
-    switch (K) {
-#define NFH_CASE(k) case k: launch_warp_variant<k>(a, grid, tiles, st); break;
-      NFH_CASE(1) NFH_CASE(2) NFH_CASE(3) NFH_CASE(4) NFH_CASE(5) NFH_CASE(6) NFH_CASE(7) NFH_CASE(8)
-      NFH_CASE(9) NFH_CASE(10) NFH_CASE(11) NFH_CASE(12) NFH_CASE(13) NFH_CASE(14) NFH_CASE(15) NFH_CASE(16)
-#undef NFH_CASE
-      default: return 1;
+  int G, K;
+  if (pick_shape(a.n_ind, G, K)) {
+    bool ok = false;
+    switch (G) {
+      case 4: ok = dispatch_k<4>(K, a, grid, st); break;
+      case 8: ok = dispatch_k<8>(K, a, grid, st); break;
+      case 16: ok = dispatch_k<16>(K, a, grid, st); break;
+      case 32: ok = dispatch_k<32>(K, a, grid, st); break;
     }
-    return 1;   // launches
+    if (ok) return 1;
   }
   unsigned blocks = (unsigned) ((a.sites_owned + kFreqThreads - 1) / kFreqThreads);
   freq_emission_stream<<<blocks ? blocks : 1, kFreqThreads, 0, st>>>(a);

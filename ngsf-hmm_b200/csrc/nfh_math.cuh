@@ -62,6 +62,13 @@ __device__ __forceinline__ double expm1_pos(double x, const double *__restrict__
 // 1/x for normal positive x: hardware seed (~2^-23) + one cubic Newton step
 // (y (1 + e + e^2), e = 1 - x y) -> error ~2^-69 before rounding, i.e. ~1 ulp.
 // With refine = true one more linear step is added (the full library sequence).
+// hardware reciprocal seed alone (relative error ~2^-23)
+__device__ __forceinline__ double rcp_seed(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+
 template <bool refine = false>
 __device__ __forceinline__ double rcp_pos(double x) {
   double y;
