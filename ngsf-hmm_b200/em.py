@@ -142,3 +142,43 @@ class EmRank:
             fr = ctx.freq_update(1, want_freq=want_freq)
             self.exchange_emissions()
         return lk, fr
+
+
+def run_em(runner: EmRank, indF, alpha, *, min_iters=10, max_iters=100, min_epsilon=1e-5, on_iteration=None):
+    """The reference's EM() loop (EM.cpp:27-135) on one rank: iterate until the stop rule of EM.cpp:56
+    fails, then decode the Viterbi path with the final parameters (EM.cpp:110-116).
+
+    indF / alpha: float64 arrays (n_ind_owned), updated in place.
+    Returns dict(iterations, tot_lkl, ind_lkl, freq, path)."""
+    n = len(indF)
+    it = 0
+    prev_tot = 0.0
+    tot = 0.0
+    max_eps = -np.inf
+    prev_ind = np.full(n, -np.inf)
+    lk = np.full(n, -np.inf)
+    fr = None
+    while ((prev_tot - tot > min_epsilon) or (max_eps > min_epsilon) or it < min_iters) and it < max_iters:
+        it += 1
+        lk, fr_new = runner.iteration(indF, alpha)
+        if fr_new is not None:
+            fr = fr_new
+        prev_tot = tot
+        tot = 0.0
+        for v in lk:                       # same left-to-right sum as EM.cpp:77
+            tot += float(v)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            eps = (lk - prev_ind) / np.abs(prev_ind)
+        # array_max_pos (gen_func.cpp:73-84): first strictly larger than -inf; NaN never wins
+        best, max_eps = 0, -np.inf
+        for i, e in enumerate(eps):
+            if e > max_eps:
+                best, max_eps = i, e
+        max_eps = eps[best]
+        prev_ind = lk.copy()
+        if on_iteration:
+            on_iteration(it, tot, max_eps)
+    runner.refresh_emissions(with_e0=True)
+    runner.ctx.set_ind_params(indF, alpha)
+    path = runner.ctx.viterbi()
+    return dict(iterations=it, tot_lkl=tot, ind_lkl=lk, freq=fr, path=path)

@@ -1,0 +1,58 @@
+// run_state.hpp - host-side state of one ngsF-HMM run (drop-in CLI).
+//
+// Mirrors what the reference keeps in its `params` struct (ngsF-HMM.hpp:13-52)
+// minus the big per-individual-site arrays, which live on the device behind
+// the C ABI (include/ngsfhmm_b200.h).
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ngsfhmm_b200.h"
+
+namespace nfh_cli {
+
+struct Options {   // one field per command-line flag of the reference (parse_args.cpp:43-68)
+  std::string geno, pos, freq_arg, indF_arg, out;
+  bool lkl = false, loglkl = false, call_geno = false, indF_fixed = false, alpha_fixed = false, log_bin = false;
+  bool in_bin = false;
+  uint64_t n_ind = 0, n_sites = 0;
+  int freq_est = 1, e_prob = 1;
+  unsigned log = 0, min_iters = 10, max_iters = 100, n_threads = 1, verbose = 1, seed = 0;
+  double min_epsilon = 1e-5;
+  bool have_geno = false, have_pos = false, have_out = false;
+  int device = 0;          // --device (extension; not a reference flag)
+};
+
+struct RunState {
+  Options opt;
+  nfh_ctx *ctx = nullptr;
+  std::vector<double> dist_mb;        // n_sites
+  std::vector<double> log_gl;         // site-major n_sites x n_ind x 3, normalised natural-log GL
+  std::vector<double> freq, indF, alpha, ind_lkl;
+  std::vector<char> path;             // n_ind x n_sites
+  std::vector<double> marg1;          // n_ind x n_sites (fetched only for output)
+  double prev_tot_lkl = 0.0, tot_lkl = 0.0;
+};
+
+// Reference-style fatal error (gen_func.cpp:12-18): message to stderr, perror, exit(-1).
+[[noreturn]] void fatal(const char *where, const char *msg);
+void warn(const char *where, const char *msg);
+void check(RunState &st, int rc, const char *where);   // maps C-ABI status to fatal()
+
+// options.cpp
+void parse_options(Options &o, int argc, char **argv);
+// ingest.cpp
+void read_positions(RunState &st);
+void read_genotypes(RunState &st);
+// startvalues.cpp
+void init_start_values(RunState &st);
+// em_loop.cpp
+void run_em(RunState &st);
+// report.cpp
+void write_outputs(RunState &st);
+
+extern const char *kVersion;
+
+}  // namespace nfh_cli

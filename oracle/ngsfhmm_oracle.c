@@ -241,6 +241,27 @@ void orc_normalize_gl(uint64_t n, double *gl) {
   }
 }
 
+/* gen_func.cpp:886-914 with the defaults main() uses (ngsF-HMM.cpp:103: log scale,
+ * both thresholds 0, miss_data 0): all-equal GLs stay missing (1/3 each), anything
+ * else becomes a hard call on the first maximum. */
+void orc_call_geno(uint64_t n, double *gl) {
+  for (uint64_t j = 0; j < n; j++) {
+    double *g = gl + 3 * j;
+    int hi = 0, lo = 0;
+    double top = -INFINITY, bot = INFINITY;
+    for (int k = 0; k < 3; k++) {
+      if (g[k] > top) { top = g[k]; hi = k; }
+      if (g[k] < bot) { bot = g[k]; lo = k; }
+    }
+    if (g[lo] == g[hi]) {
+      for (int k = 0; k < 3; k++) g[k] = log((double) 1 / 3);
+    } else {
+      for (int k = 0; k < 3; k++) g[k] = -ORC_INF;
+      g[hi] = log(1);
+    }
+  }
+}
+
 /* Not in the reference: scaled linear-space forward-backward in long double. */
 void orc_estep_extended(uint64_t S, const double *e_prob, const double *dist, double F, double alpha,
                         double *marg1_unclamped, double *lkl) {

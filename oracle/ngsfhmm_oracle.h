@@ -69,6 +69,9 @@ void orc_freq_emission(uint64_t N, uint64_t S, const double *gl, const double *m
 /* read_data.cpp:37-40 + ngsF-HMM.cpp:116: normalise n x 3 log GL in place (applied twice, as the reference does) */
 void orc_normalize_gl(uint64_t n, double *gl);
 
+/* gen_func.cpp:886-914 with main()'s defaults (ngsF-HMM.cpp:103); n x 3 log GL in place */
+void orc_call_geno(uint64_t n, double *gl);
+
 /* Extended-precision adjudicator (not in the reference): the same E-step in
  * scaled linear space with long double accumulation.  Used only to decide
  * which side is noisier when log-space double noise exceeds the tolerance at

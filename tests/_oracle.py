@@ -70,6 +70,7 @@ class Oracle:
         L.orc_estep.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _dp, _dp]
         L.orc_freq_emission.argtypes = [C.c_uint64, C.c_uint64, _dp, _dp, C.c_int, _dp, _dp]
         L.orc_normalize_gl.argtypes = [C.c_uint64, _dp]
+        L.orc_call_geno.argtypes = [C.c_uint64, _dp]
         L.orc_estep_extended.argtypes = [C.c_uint64, _dp, _dp, C.c_double, C.c_double, _dp, _dp]
 
     # --- scalar helpers
@@ -125,10 +126,23 @@ class Oracle:
         self.lib.orc_freq_emission(N, S, _d(g), _d(m), int(update_freq), _d(fr), _d(e))
         return fr, e
 
-    def normalize_gl(self, gl):
+    def normalize_gl(self, gl, call_geno=False):
+        """What read_geno + main() do to raw log GL: normalise, optionally call genotypes, normalise."""
         g = f64(gl).copy()
-        self.lib.orc_normalize_gl(g.size // 3, _d(g))
+        n = g.size // 3
+        if call_geno:
+            # read_geno normalises once, main() calls genotypes, then normalises again
+            one = Oracle._norm_once(g)
+            self.lib.orc_call_geno(n, _d(one))
+            return Oracle._norm_once(one)
+        self.lib.orc_normalize_gl(n, _d(g))
         return g
+
+    @staticmethod
+    def _norm_once(g):
+        m = g.max(axis=-1, keepdims=True)
+        with np.errstate(divide="ignore"):
+            return g - (np.log(np.exp(g - m).sum(axis=-1, keepdims=True)) + m)
 
     def estep_extended(self, e_prob, dist, F, alpha):
         e = f64(e_prob); d = f64(dist); S = len(d)

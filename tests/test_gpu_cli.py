@@ -1,0 +1,124 @@
+"""GPU: the drop-in command-line binary against the unmodified reference binary (prebuilt oracle/_ref)
+on the same input files and flags; output files compared field by field."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import ngsf_hmm_b200  # noqa: F401
+from ngsf_hmm_b200 import sim
+
+pytestmark = [pytest.mark.gpu, pytest.mark.ref]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "ngsf-hmm_b200", "ngsF-HMM")
+REF = os.path.join(ROOT, "oracle", "_ref", "ngsF-HMM")
+
+
+def _run(binary, args, cwd):
+    p = subprocess.run([binary] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def _parse_indF(path, n_ind):
+    lines = open(path).read().split("\n")
+    tot = float(lines[0])
+    F, a = [], []
+    for ln in lines[1:1 + n_ind]:
+        f, al = ln.split("\t")
+        F.append(float(f)); a.append(np.nan if al == "NA" else float(al))
+    freq = np.array([float(x) for x in lines[1 + n_ind:] if x])
+    return tot, np.array(F), np.array(a), freq
+
+
+def _parse_ibd(path, n_ind):
+    lines = open(path).read().split("\n")
+    lkl = np.array([float(x) for x in lines[0].split("\t")[1:]])
+    paths = np.array([[int(c) for c in ln] for ln in lines[1:1 + n_ind]], dtype=np.int8)
+    marg = np.array([[float(x) for x in ln.split("\t")] for ln in lines[1 + n_ind:1 + 2 * n_ind]])
+    return lkl, paths, marg
+
+
+def _compare(tmp, n_ind, n_sites, f_tol=2e-5):
+    tot_r, F_r, a_r, fr_r = _parse_indF(str(tmp / "ref.indF"), n_ind)
+    tot_o, F_o, a_o, fr_o = _parse_indF(str(tmp / "ours.indF"), n_ind)
+    assert abs(tot_o - tot_r) <= 1e-9 * abs(tot_r) + 1e-9
+    np.testing.assert_allclose(F_o, F_r, rtol=0, atol=f_tol)
+    assert (np.isnan(a_o) == np.isnan(a_r)).all()
+    np.testing.assert_allclose(np.nan_to_num(a_o), np.nan_to_num(a_r), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(fr_o, fr_r, rtol=0, atol=2e-6)
+    lk_r, p_r, m_r = _parse_ibd(str(tmp / "ref.ibd"), n_ind)
+    lk_o, p_o, m_o = _parse_ibd(str(tmp / "ours.ibd"), n_ind)
+    np.testing.assert_allclose(lk_o, lk_r, rtol=1e-9, atol=1e-9)
+    assert p_o.shape == (n_ind, n_sites) and (p_o != p_r).sum() == 0
+    assert np.abs(m_o - m_r).max() <= 1.1e-5          # %f print + clamp flips
+    assert (np.abs(m_o - m_r) > 2e-6).mean() < 1e-3
+    g_r = np.fromfile(str(tmp / "ref.geno")); g_o = np.fromfile(str(tmp / "ours.geno"))
+    assert g_r.shape == g_o.shape == (n_sites * n_ind * 3,)
+    np.testing.assert_allclose(g_o, g_r, rtol=0, atol=1e-6)
+
+
+def test_beagle_gz_lkl_freq_est_1(tmp_path):
+    """BASELINE configs[0] input style: BEAGLE gz text with linear GLs, --lkl --freq_est 1."""
+    N, S = 8, 3000
+    d = sim.simulate(N, S, seed=4242, freq=0.2, indF=0.5, alpha=0.01, depth=2.0)
+    sim.write_beagle_gz(str(tmp_path / "in.beagle.gz"), d.log_gl, d.pos_bp)
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    common = ["--geno", "in.beagle.gz", "--lkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos",
+              "--freq", "0.1", "--indF", "0.1,0.2", "--freq_est", "1", "--min_iters", "3", "--max_iters", "4",
+              "--seed", "1", "--verbose", "1"]
+    _run(REF, common + ["--out", "ref", "--n_threads", "4"], str(tmp_path))
+    out = _run(OURS, common + ["--out", "ours"], str(tmp_path))
+    assert "Iteration 3:" in out and "Final logLkl" in out
+    _compare(tmp_path, N, S)
+
+
+def test_binary_loglkl_fixed_parameters_two_chromosomes(tmp_path):
+    """Raw-double log GL, parameters fixed (posterior + Viterbi only), a chromosome change in --pos."""
+    N, S = 5, 2500
+    d = sim.simulate(N, S, seed=777, freq=(0.05, 0.5), indF=(0.1, 0.6), alpha=0.05)
+    sim.write_binary_gl(str(tmp_path / "in.glf"), d.log_gl)
+    with open(str(tmp_path / "in.pos"), "w") as fh:
+        for s in range(S):
+            chrom = "chr1" if s < 1200 else "chr2"
+            pos = int(d.pos_bp[s]) if s < 1200 else int(d.pos_bp[s] - d.pos_bp[1199])
+            fh.write(f"{chrom}\t{pos}\n")
+    np.savetxt(str(tmp_path / "freq.txt"), np.clip(d.true_freq, 0.01, 0.49), fmt="%.6f")
+    with open(str(tmp_path / "indF.txt"), "w") as fh:
+        for i in range(N):
+            fh.write(f"{max(d.true_F[i], 1e-3):.6f}\t{d.true_alpha[i]:.6f}\n")
+    common = ["--geno", "in.glf", "--loglkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos",
+              "--freq", "freq.txt", "--freq_est", "0", "--indF", "indF.txt", "--indF_fixed", "--alpha_fixed",
+              "--min_iters", "1", "--max_iters", "2", "--verbose", "0"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    _run(OURS, common + ["--out", "ours"], str(tmp_path))
+    _compare(tmp_path, N, S, f_tol=1e-9)
+
+
+def test_called_genotypes_and_estimated_start_frequencies(tmp_path):
+    """Called-genotype text input (no --lkl) with --freq e (est_maf with F = 0 on the device)."""
+    N, S = 6, 2000
+    d = sim.simulate(N, S, seed=31337, freq=(0.1, 0.5), indF=(0.1, 0.6), alpha=0.02, depth=20.0)
+    sim.write_geno_gz(str(tmp_path / "in.geno.gz"), d.geno)
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    common = ["--geno", "in.geno.gz", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "e",
+              "--indF", "0.1,0.2", "--min_iters", "2", "--max_iters", "3", "--verbose", "0"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    _run(OURS, common + ["--out", "ours"], str(tmp_path))
+    _compare(tmp_path, N, S, f_tol=5e-5)
+
+
+def test_error_behaviour_matches_reference(tmp_path):
+    """Missing --pos and a truncated GENO file end with the reference's messages and a non-zero status."""
+    p = subprocess.run([OURS, "--geno", "x.gz", "--n_ind", "2", "--n_sites", "3", "--out", "o"], cwd=str(tmp_path),
+                       capture_output=True, text=True)
+    assert p.returncode != 0 and "positions input file (--pos) missing!" in p.stderr
+    N, S = 2, 50
+    d = sim.simulate(N, S, seed=5)
+    sim.write_binary_gl(str(tmp_path / "short.glf"), d.log_gl[:40])
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    p = subprocess.run([OURS, "--geno", "short.glf", "--loglkl", "--n_ind", str(N), "--n_sites", str(S), "--pos",
+                        "in.pos", "--out", "o", "--freq", "0.1"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode != 0 and "invalid/corrupt genotype input file!" in p.stderr
