@@ -173,6 +173,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     n_ranks = world
     N_total, S = args.n_ind * n_ranks, args.n_sites
