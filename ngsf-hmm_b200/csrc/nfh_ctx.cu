@@ -39,8 +39,8 @@ struct nfh_ctx {
   // recursion side (this rank's individuals, all sites, site-blocked layout)
   double *dist = nullptr, *emis_recv = nullptr, *post_send = nullptr, *e0_recv = nullptr;
   double *indF = nullptr, *alpha = nullptr, *ind_lkl = nullptr;
-  ChunkProd *chunk_prod = nullptr;
-  TileProd *lkl_tile_prod = nullptr;
+  double4 *chunk_prod = nullptr;
+  TileProd *tile_prod = nullptr, *lkl_tile_prod = nullptr;
   double2 *fwd_carry = nullptr, *bwd_carry = nullptr;
   LklGroup *groups = nullptr;
   double *neg_lkl = nullptr;
@@ -207,10 +207,11 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   NFH_TRY(alloc((void **) &ctx->alpha, ctx->n_loc * sizeof(double), true));
   NFH_TRY(alloc((void **) &ctx->ind_lkl, ctx->n_loc * sizeof(double), true));
   const size_t n_chunks = (size_t) ctx->n_tiles * kScanThreads;
-  NFH_TRY(alloc((void **) &ctx->chunk_prod, ctx->n_loc * n_chunks * sizeof(ChunkProd), false));
+  NFH_TRY(alloc((void **) &ctx->chunk_prod, ctx->n_loc * n_chunks * sizeof(double4), false));
+  NFH_TRY(alloc((void **) &ctx->tile_prod, ctx->n_loc * ctx->n_tiles * sizeof(TileProd), false));
   NFH_TRY(alloc((void **) &ctx->lkl_tile_prod, ctx->n_loc * kMaxPoints * ctx->n_tiles * sizeof(TileProd), false));
-  NFH_TRY(alloc((void **) &ctx->fwd_carry, ctx->n_loc * n_chunks * sizeof(double2), false));
-  NFH_TRY(alloc((void **) &ctx->bwd_carry, ctx->n_loc * n_chunks * sizeof(double2), false));
+  NFH_TRY(alloc((void **) &ctx->fwd_carry, ctx->n_loc * ctx->n_tiles * sizeof(double2), false));
+  NFH_TRY(alloc((void **) &ctx->bwd_carry, ctx->n_loc * ctx->n_tiles * sizeof(double2), false));
   NFH_TRY(alloc((void **) &ctx->groups, ctx->n_loc * sizeof(LklGroup), false));
   NFH_TRY(alloc((void **) &ctx->neg_lkl, ctx->n_loc * kMaxPoints * sizeof(double), false));
   for (int g = 0; g < 3; g++) NFH_TRY(alloc((void **) &ctx->gl[g], plane_frq, true));
@@ -247,7 +248,7 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
-                 ctx->chunk_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
+                 ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
                  ctx->vit_work, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
                  ctx->status, ctx->d_stage};
   for (void *p : dev) if (p) cudaFree(p);
@@ -395,7 +396,7 @@ int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out) {
     EstepArgs a;
     a.emis = ctx->emis_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
     a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
-    a.chunk_prod = ctx->chunk_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
+    a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
     a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
     a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
     a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;

@@ -10,12 +10,15 @@
 // E-step = three launches:
 //   estep_chunk_products : every thread reduces its 33 consecutive sites to one
 //                          scaled 2x2 product (tile staged in shared memory by TMA).
-//   estep_chunk_scan     : per individual, scan over the chunk products: forward
-//                          carry into and backward carry out of every chunk, and
+//                          The CTA also reduces its 128 chunk products to one tile product.
+//   estep_tile_carries   : per individual, chain of the tile products: forward
+//                          carry into and backward carry out of every tile, and
 //                          the log-likelihood computed both ways.
-//   estep_chunk_apply    : every thread re-reads its 33 sites (TMA-staged), runs
-//                          the forward and the backward vector recursion from its
-//                          carries and writes the clamped IBD posterior (TMA store).
+//   estep_chunk_apply    : the CTA turns the tile carries plus its 128 chunk products
+//                          into per-chunk carries (warp scans), then every thread
+//                          re-reads its 33 sites (TMA-staged), runs the forward and
+//                          the backward vector recursion and writes the clamped IBD
+//                          posterior (TMA store).
 // HBM traffic per individual-site: 8 B + 8 B of emission ratio read, 8 B of
 // posterior written, ~2.4 B of chunk products/carries; site distances come
 // from L2.
@@ -56,8 +59,9 @@ __device__ __forceinline__ int valid_sites(uint64_t first_site, uint64_t n_sites
 
 __global__ void __launch_bounds__(kScanThreads)
 estep_chunk_products(const double *__restrict__ emis, const double *__restrict__ dist, const double *__restrict__ indF,
-                     const double *__restrict__ alpha, ChunkProd *__restrict__ chunk_prod, uint64_t n_rows,
-                     uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+                     const double *__restrict__ alpha, double4 *__restrict__ chunk_prod,
+                     TileProd *__restrict__ tile_prod, uint64_t n_rows, uint64_t n_sites, uint64_t site_block,
+                     uint32_t n_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const uint32_t tile = blockIdx.x, row = blockIdx.y;
@@ -82,112 +86,180 @@ estep_chunk_products(const double *__restrict__ emis, const double *__restrict__
     if (j % 6 == 5) e += renorm(m);
   }
   e += renorm(m);
-  ChunkProd out;
-  out.a = m.a; out.b = m.b; out.c = m.c; out.d = m.d; out.e = (double) e; out.l = ls;
-  chunk_prod[((size_t) row * n_tiles + tile) * kScanThreads + threadIdx.x] = out;
+  // per-chunk product (direction only: the apply kernel is scale free)
+  chunk_prod[((size_t) row * n_tiles + tile) * kScanThreads + threadIdx.x] = make_double4(m.a, m.b, m.c, m.d);
+
+  // per-tile product with its scale, for the carry kernel and the log-likelihood
+  __shared__ M2 sm_m[kScanThreads / 32];
+  __shared__ int sm_e[kScanThreads / 32];
+  __shared__ double sm_l[kScanThreads / 32];
+  warp_ordered_product(m, e);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ls += __shfl_down_sync(kFull, ls, off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sm_m[warp] = m; sm_e[warp] = e; sm_l[warp] = ls; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    M2 acc = sm_m[0];
+    int ae = sm_e[0];
+    double al_sum = sm_l[0];
+#pragma unroll
+    for (int w = 1; w < kScanThreads / 32; w++) {
+      acc = matmul(acc, sm_m[w]);
+      ae += sm_e[w] + renorm(acc);
+      al_sum += sm_l[w];
+    }
+    TileProd out;
+    out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae; out.l = al_sum;
+    tile_prod[(size_t) row * n_tiles + tile] = out;
+  }
 }
 
-// vector-matrix and matrix-vector steps with renormalisation
-__device__ __forceinline__ int step_fwd(double &x0, double &x1, const ChunkProd &p) {
-  const double y0 = fma(x0, p.a, x1 * p.c), y1 = fma(x0, p.b, x1 * p.d);
-  x0 = y0; x1 = y1;
-  return renorm2(x0, x1);
-}
-__device__ __forceinline__ int step_bwd(double &b0, double &b1, const ChunkProd &p) {
-  const double y0 = fma(p.a, b0, p.b * b1), y1 = fma(p.c, b0, p.d * b1);
-  b0 = y0; b1 = y1;
-  return renorm2(b0, b1);
-}
-
-// One CTA per individual.  Thread t owns a contiguous run of chunk products.
-//   pass 1: product of the run (as a 2x2 with exponent) -> shared memory
-//   middle: two threads chain the 256 run products, forwards and backwards
-//   pass 2: every thread walks its run again, writing the carry of each chunk
-constexpr int kCarryThreads = 256;
-
-__global__ void __launch_bounds__(kCarryThreads)
-estep_chunk_scan(const ChunkProd *__restrict__ chunk_prod, const double *__restrict__ indF,
-                 const double *__restrict__ loge0_sum, double2 *__restrict__ fwd_carry,
-                 double2 *__restrict__ bwd_carry, double *__restrict__ ind_lkl, int *__restrict__ status,
-                 uint32_t n_chunks) {
-  const uint32_t row = blockIdx.x;
+// One warp per individual.  Tiles are taken 32 at a time: a coalesced load, an
+// inclusive warp scan of the 2x2 products (with exponents), and the running
+// vector gives the carry of each of the 32 tiles; forwards from q, then
+// backwards from 1.  Also the log-likelihood both ways (EM.cpp:166).
+__global__ void __launch_bounds__(128)
+estep_tile_carries(const TileProd *__restrict__ tile_prod, const double *__restrict__ indF,
+                   const double *__restrict__ loge0_sum, double2 *__restrict__ fwd_carry,
+                   double2 *__restrict__ bwd_carry, double *__restrict__ ind_lkl, int *__restrict__ status,
+                   uint32_t n_rows_valid, uint32_t n_tiles) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows_valid) return;                       // warp-uniform
   const double F = indF[row];
   const double q0 = 1.0 - F, q1 = F;
-  const ChunkProd *cp = chunk_prod + (size_t) row * n_chunks;
-  double2 *fc = fwd_carry + (size_t) row * n_chunks;
-  double2 *bc = bwd_carry + (size_t) row * n_chunks;
+  const TileProd *tp = tile_prod + (size_t) row * n_tiles;
+  double2 *fc = fwd_carry + (size_t) row * n_tiles;
+  double2 *bc = bwd_carry + (size_t) row * n_tiles;
+  const uint32_t n_groups = (n_tiles + 31) / 32;
 
-  const uint32_t per = (n_chunks + kCarryThreads - 1) / kCarryThreads;
-  const uint32_t lo = min(n_chunks, threadIdx.x * per), hi = min(n_chunks, lo + per);
-
-  __shared__ ChunkProd run[kCarryThreads];
-  __shared__ double2 run_in[kCarryThreads], run_out[kCarryThreads];
-  __shared__ double lkl_both[2];
-
-  {
+  // ---- forwards
+  double x0 = q0, x1 = q1, lsum = 0.0;
+  long long ex = 0;
+  for (uint32_t g = 0; g < n_groups; g++) {
+    const uint32_t t = g * 32 + lane;
     M2 m = identity2();
-    long long e = 0;
+    int e = 0;
     double l = 0.0;
-    for (uint32_t c = lo; c < hi; c++) {
-      const ChunkProd p = cp[c];
-      M2 o; o.a = p.a; o.b = p.b; o.c = p.c; o.d = p.d;
-      m = matmul(m, o);
-      e += (long long) p.e + renorm(m);
-      l += p.l;
+    if (t < n_tiles) {
+      const TileProd p = tp[t];
+      m.a = p.a; m.b = p.b; m.c = p.c; m.d = p.d; e = (int) p.e; l = p.l;
     }
-    ChunkProd t;
-    t.a = m.a; t.b = m.b; t.c = m.c; t.d = m.d; t.e = (double) e; t.l = l;
-    run[threadIdx.x] = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const M2 o = shfl_up_m(m, off);
+      const int oe = __shfl_up_sync(kFull, e, off);
+      if (lane >= off) { m = matmul(o, m); e += oe + renorm(m); }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(kFull, l, off);
+    lsum += l;
+    const M2 before = shfl_up_m(m, 1);
+    double c0 = x0, c1 = x1;
+    if (lane > 0) { c0 = fma(x0, before.a, x1 * before.c); c1 = fma(x0, before.b, x1 * before.d); renorm2(c0, c1); }
+    if (t < n_tiles) fc[t] = make_double2(c0, c1);
+    M2 tot;
+    tot.a = __shfl_sync(kFull, m.a, 31); tot.b = __shfl_sync(kFull, m.b, 31);
+    tot.c = __shfl_sync(kFull, m.c, 31); tot.d = __shfl_sync(kFull, m.d, 31);
+    const int te = __shfl_sync(kFull, e, 31);
+    const double y0 = fma(x0, tot.a, x1 * tot.c), y1 = fma(x0, tot.b, x1 * tot.d);
+    x0 = y0; x1 = y1;
+    ex += te + renorm2(x0, x1);
   }
-  __syncthreads();
+  const double base = lsum + loge0_sum[row];
+  const double lf = log(x0 + x1) + (double) ex * kLn2 + base;
 
-  if (threadIdx.x == 0) {
-    double x0 = q0, x1 = q1, e = 0.0, l = 0.0;
-    for (int t = 0; t < kCarryThreads; t++) {
-      run_in[t] = make_double2(x0, x1);
-      const ChunkProd p = run[t];
-      e += p.e + step_fwd(x0, x1, p);
-      l += p.l;
+  // ---- backwards
+  double b0 = 1.0, b1 = 1.0;
+  long long eb = 0;
+  for (uint32_t g = n_groups; g-- > 0;) {
+    const uint32_t t = g * 32 + lane;
+    M2 m = identity2();
+    int e = 0;
+    if (t < n_tiles) {
+      const TileProd p = tp[t];
+      m.a = p.a; m.b = p.b; m.c = p.c; m.d = p.d; e = (int) p.e;
     }
-    const double lf = log(x0 + x1) + e * kLn2 + l + loge0_sum[row];
-    ind_lkl[row] = lf;
-    lkl_both[0] = lf;
-  } else if (threadIdx.x == 32) {
-    double b0 = 1.0, b1 = 1.0, e = 0.0, l = 0.0;
-    for (int t = kCarryThreads - 1; t >= 0; t--) {
-      run_out[t] = make_double2(b0, b1);
-      const ChunkProd p = run[t];
-      e += p.e + step_bwd(b0, b1, p);
-      l += p.l;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {             // inclusive suffix: P_t ... P_{last of group}
+      const M2 o = shfl_down_m(m, off);
+      const int oe = __shfl_down_sync(kFull, e, off);
+      if (lane + off < 32) { m = matmul(m, o); e += oe + renorm(m); }
     }
-    lkl_both[1] = log(fma(q0, b0, q1 * b1)) + e * kLn2 + l + loge0_sum[row];
+    const M2 after = shfl_down_m(m, 1);
+    double c0 = b0, c1 = b1;
+    if (lane < 31) { c0 = fma(after.a, b0, after.b * b1); c1 = fma(after.c, b0, after.d * b1); renorm2(c0, c1); }
+    if (t < n_tiles) bc[t] = make_double2(c0, c1);
+    M2 tot;
+    tot.a = __shfl_sync(kFull, m.a, 0); tot.b = __shfl_sync(kFull, m.b, 0);
+    tot.c = __shfl_sync(kFull, m.c, 0); tot.d = __shfl_sync(kFull, m.d, 0);
+    const int te = __shfl_sync(kFull, e, 0);
+    const double y0 = fma(tot.a, b0, tot.b * b1), y1 = fma(tot.c, b0, tot.d * b1);
+    b0 = y0; b1 = y1;
+    eb += te + renorm2(b0, b1);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const double lf = lkl_both[0], lb = lkl_both[1];
+  const double lb = log(fma(q0, b0, q1 * b1)) + (double) eb * kLn2 + base;
+
+  if (lane == 0) {
+    ind_lkl[row] = lf;
     if (lf != lf || lb != lb) atomicOr(status, kFlagNaN);
     else if (fabs(lf - lb) > 1e-3) atomicOr(status, kFlagFwBw);   // EM.cpp:166
   }
+}
 
-  {
-    double x0 = run_in[threadIdx.x].x, x1 = run_in[threadIdx.x].y;
-    for (uint32_t c = lo; c < hi; c++) {
-      fc[c] = make_double2(x0, x1);
-      step_fwd(x0, x1, cp[c]);
-    }
-    double b0 = run_out[threadIdx.x].x, b1 = run_out[threadIdx.x].y;
-    for (uint32_t c = hi; c-- > lo;) {
-      bc[c] = make_double2(b0, b1);
-      step_bwd(b0, b1, cp[c]);
-    }
+// Carries of this thread's chunk from the tile carries and the tile's 128
+// chunk products: warp prefix/suffix scans (direction only) plus a 4-way
+// combine through shared memory.
+__device__ __forceinline__ void chunk_carries(const double4 *__restrict__ chunk_prod_tile, double2 tile_fwd,
+                                              double2 tile_bwd, double &a0, double &a1, double &b0, double &b1) {
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ M2 warp_tot[kWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double4 mine4 = chunk_prod_tile[threadIdx.x];
+  M2 mine; mine.a = mine4.x; mine.b = mine4.y; mine.c = mine4.z; mine.d = mine4.w;
+  M2 pre = mine, suf = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    M2 o = shfl_up_m(pre, off);
+    if (lane >= off) { pre = matmul(o, pre); renorm(pre); }
+    M2 u = shfl_down_m(suf, off);
+    if (lane + off < 32) { suf = matmul(suf, u); renorm(suf); }
+  }
+  if (lane == 31) warp_tot[warp] = pre;
+  __syncthreads();
+  a0 = tile_fwd.x; a1 = tile_fwd.y;
+  for (int w = 0; w < warp; w++) {                 // warp-uniform trip count
+    const M2 p = warp_tot[w];
+    const double y0 = fma(a0, p.a, a1 * p.c), y1 = fma(a0, p.b, a1 * p.d);
+    a0 = y0; a1 = y1;
+    renorm2(a0, a1);
+  }
+  b0 = tile_bwd.x; b1 = tile_bwd.y;
+  for (int w = kWarps - 1; w > warp; w--) {
+    const M2 p = warp_tot[w];
+    const double y0 = fma(p.a, b0, p.b * b1), y1 = fma(p.c, b0, p.d * b1);
+    b0 = y0; b1 = y1;
+    renorm2(b0, b1);
+  }
+  const M2 before = shfl_up_m(pre, 1);     // product of lanes < me (valid for lane > 0)
+  const M2 after = shfl_down_m(suf, 1);    // product of lanes > me (valid for lane < 31)
+  if (lane > 0) {
+    const double y0 = fma(a0, before.a, a1 * before.c), y1 = fma(a0, before.b, a1 * before.d);
+    a0 = y0; a1 = y1;
+  }
+  if (lane < 31) {
+    const double y0 = fma(after.a, b0, after.b * b1), y1 = fma(after.c, b0, after.d * b1);
+    b0 = y0; b1 = y1;
   }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ dist, const double *__restrict__ indF,
-                  const double *__restrict__ alpha, const double2 *__restrict__ fwd_carry,
-                  const double2 *__restrict__ bwd_carry, double *__restrict__ post, int *__restrict__ status,
-                  uint64_t n_rows, uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+                  const double *__restrict__ alpha, const double4 *__restrict__ chunk_prod,
+                  const double2 *__restrict__ fwd_carry, const double2 *__restrict__ bwd_carry,
+                  double *__restrict__ post, int *__restrict__ status, uint64_t n_rows, uint64_t n_sites,
+                  uint64_t site_block, uint32_t n_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const uint32_t tile = blockIdx.x, row = blockIdx.y;
@@ -200,12 +272,13 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
   const double q0 = 1.0 - F, q1 = F;
   double *r = sm.r + threadIdx.x * kChunk;     // becomes the posterior
   double *d = sm.d + threadIdx.x * kChunk;     // becomes kappa
-  const size_t chunk = ((size_t) row * n_tiles + tile) * kScanThreads + threadIdx.x;
-  const double2 cf = fwd_carry[chunk], cb = bwd_carry[chunk];
+  double cf0, cf1, cb0, cb1;
+  chunk_carries(chunk_prod + ((size_t) row * n_tiles + tile) * kScanThreads, fwd_carry[(size_t) row * n_tiles + tile],
+                bwd_carry[(size_t) row * n_tiles + tile], cf0, cf1, cb0, cb1);
 
   // sweep 1: kappa for every site (kept in shared memory) and the forward
   // vector at the start of each sub-block (checkpoints, also in shared memory)
-  double a0 = cf.x, a1 = cf.y;
+  double a0 = cf0, a1 = cf1;
   double2 *ck = sm.ck + threadIdx.x * (kChunk / kSub);
 #pragma unroll 1
   for (int sb = 0; sb < kChunk / kSub; sb++) {
@@ -223,7 +296,7 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
 
   // sweep 2, sub-blocks from the right: rebuild the forward vectors of the
   // sub-block in registers, then run the backward vector through it.
-  double b0 = cb.x, b1 = cb.y;
+  double b0 = cb0, b1 = cb1;
   bool bad = false;
 #pragma unroll 1
   for (int sb = kChunk / kSub - 1; sb >= 0; sb--) {
@@ -411,12 +484,14 @@ void launch_estep(const EstepArgs &a, cudaStream_t st) {
   set_smem_attrs();
   dim3 grid(a.n_tiles, (unsigned) a.n_rows_valid);
   estep_chunk_products<<<grid, kScanThreads, sizeof(TileSmem), st>>>(a.emis, a.dist, a.indF, a.alpha, a.chunk_prod,
-                                                                     a.n_rows, a.n_sites, a.site_block, a.n_tiles);
-  estep_chunk_scan<<<(unsigned) a.n_rows_valid, kCarryThreads, 0, st>>>(
-      a.chunk_prod, a.indF, a.loge0_sum, a.fwd_carry, a.bwd_carry, a.ind_lkl, a.status, a.n_tiles * kScanThreads);
-  estep_chunk_apply<<<grid, kScanThreads, sizeof(TileSmem), st>>>(a.emis, a.dist, a.indF, a.alpha, a.fwd_carry,
-                                                                  a.bwd_carry, a.post, a.status, a.n_rows, a.n_sites,
-                                                                  a.site_block, a.n_tiles);
+                                                                     a.tile_prod, a.n_rows, a.n_sites, a.site_block,
+                                                                     a.n_tiles);
+  estep_tile_carries<<<(unsigned) ((a.n_rows_valid + 3) / 4), 128, 0, st>>>(
+      a.tile_prod, a.indF, a.loge0_sum, a.fwd_carry, a.bwd_carry, a.ind_lkl, a.status, (uint32_t) a.n_rows_valid,
+      a.n_tiles);
+  estep_chunk_apply<<<grid, kScanThreads, sizeof(TileSmem), st>>>(a.emis, a.dist, a.indF, a.alpha, a.chunk_prod,
+                                                                  a.fwd_carry, a.bwd_carry, a.post, a.status, a.n_rows,
+                                                                  a.n_sites, a.site_block, a.n_tiles);
 }
 
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st) {

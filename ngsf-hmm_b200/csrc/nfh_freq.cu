@@ -210,6 +210,121 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
   }
 }
 
+// Teams of W warps share one site (32 W lanes, K individuals per lane): the
+// register-resident scheme for 128 < n_ind <= 4096, e.g. the frequency side of
+// a multi-rank run, which always sees ALL individuals.  Per pass the lanes of a
+// warp reduce by shuffles, the W warps of a team through shared memory (one
+// barrier per pass, partials double-buffered by pass parity).
+constexpr int kTeamThreads = 256;
+
+template <int W, int K>
+__global__ void __launch_bounds__(kTeamThreads)
+freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
+  constexpr int kWarps = kTeamThreads / 32;
+  constexpr int kTeams = kWarps / W;
+  constexpr int G = 32 * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / W, wt = warp % W;
+  const int grp = wt * 32 + lane;
+  extern __shared__ double team_smem[];                 // [kTeams][n_ind_pad] log e0 accumulators
+  __shared__ double2 part[2][kTeams][W];
+  __shared__ double gpart[kTeams][W];
+  for (unsigned i = threadIdx.x; i < kTeams * A.n_ind_pad; i += kTeamThreads) team_smem[i] = 0.0;
+  __syncthreads();
+  double *my_acc = team_smem + (size_t) team * A.n_ind_pad;
+
+  for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x) {
+    const uint64_t site = (uint64_t) tile * kTeams + team;
+    const bool site_ok = site < A.sites_owned;
+    const uint64_t sl = site_ok ? site : 0;
+
+    double a0[K], a2[K], hh[K], na[K], nv[K], da[K];
+    double g_sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      IndCoef c;
+      if (i < A.n_ind) {
+        const size_t at = (size_t) i * A.site_block + sl;
+        const double F = A.post ? A.post[at] : 0.0;
+        c = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
+      } else {
+        c = null_coef();
+      }
+      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; da[k] = c.da;
+      g_sum += c.g;
+    }
+
+    double freq = A.update_freq ? 0.01 : A.freq[sl];
+    if (A.update_freq) {
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
+      if (lane == 0) gpart[team][wt] = g_sum;
+      __syncthreads();
+      g_sum = 0.0;
+#pragma unroll
+      for (int w = 0; w < W; w++) g_sum += gpart[team][w];
+
+      double num = 0.0, den = 0.0;
+      bool active = site_ok;
+      int passes = 0;
+      while (__syncthreads_or(active)) {                // also orders the previous pass's reads before new writes
+        const double omf = 1.0 - freq;
+        const double u = omf * omf, v = freq * freq, a = omf * freq;
+        double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const double S = fma(a0[k], u, fma(a2[k], v, hh[k] * a));
+          const double rinv = rcp_pos(S);
+          if (k & 1) { B1 = fma(na[k], rinv, B1); B2 = fma(nv[k], rinv, B2); B3 = fma(da[k], rinv, B3); }
+          else       { A1 = fma(na[k], rinv, A1); A2 = fma(nv[k], rinv, A2); A3 = fma(da[k], rinv, A3); }
+        }
+        double pn = fma(a, A1 + B1, v * (A2 + B2));
+        double pd = a * (A3 + B3);
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) {
+          pn += __shfl_xor_sync(kFull, pn, m);
+          pd += __shfl_xor_sync(kFull, pd, m);
+        }
+        const int buf = passes & 1;
+        if (lane == 0) part[buf][team][wt] = make_double2(pn, pd);
+        __syncthreads();
+        pn = 0.0; pd = g_sum;
+#pragma unroll
+        for (int w = 0; w < W; w++) { const double2 q = part[buf][team][w]; pn += q.x; pd += q.y; }
+        passes++;
+        if (active) {
+          num += pn; den += pd;
+          const double before = freq;
+          freq = num * rcp_pos<true>(den);
+          active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
+        }
+      }
+      if (site_ok && grp == 0) A.freq[site] = freq;
+    }
+
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      if (i < A.n_ind && site_ok) {
+        const size_t at = (size_t) i * A.site_block + site;
+        double e0, e1;
+        emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
+        A.emis[at] = e1 / e0;
+        if (A.e0) A.e0[at] = e0;
+        my_acc[i] += log(e0);                           // each (team, individual) slot has one writer
+      }
+    }
+  }
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kTeamThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < kTeams; t++) s += team_smem[(size_t) t * A.n_ind_pad + i];
+    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = s;
+  }
+}
+
 // Any number of individuals: one thread per site walks the individuals in
 // index order every pass (the reference's own summation order), re-reading GL
 // and posterior through L2.  Slow path for n_ind beyond the register variants.
@@ -362,10 +477,22 @@ static bool pick_shape(uint64_t n_ind, int &G, int &K) {
   return best_g != 0;
 }
 
+// Team variant: fewest warps per site W in {2,4,8} with K = ceil(n / 32W) <= 13 (else <= 16).
+static bool pick_team_shape(uint64_t n_ind, int &W, int &K) {
+  for (int cap : {13, kMaxK})
+    for (int w = 2; w <= 8; w <<= 1) {
+      const int k = (int) ((n_ind + 32 * w - 1) / (32 * w));
+      if (k >= 1 && k <= cap) { W = w; K = k; return true; }
+    }
+  return false;
+}
+
 unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
-  int G, K;
-  if (pick_shape(a.n_ind, G, K)) {
-    const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
+  int G, K, W;
+  unsigned per_cta = 0;
+  if (pick_shape(a.n_ind, G, K)) per_cta = (32 / G) * (kFreqThreads / 32);
+  else if (pick_team_shape(a.n_ind, W, K)) per_cta = (kTeamThreads / 32) / W;
+  if (per_cta) {
     unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
     unsigned cap = (unsigned) sm_count * 4u;
     return tiles < cap ? (tiles ? tiles : 1u) : cap;
@@ -381,19 +508,45 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   freq_emission_warp<G, K><<<grid, kFreqThreads, smem, st>>>(a, tiles);
 }
 
+template <int W, int K>
+static void launch_team_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  constexpr int kTeams = (kTeamThreads / 32) / W;
+  const unsigned tiles = (unsigned) ((a.sites_owned + kTeams - 1) / kTeams);
+  size_t smem = (size_t) kTeams * a.n_ind_pad * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(freq_emission_team<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  freq_emission_team<W, K><<<grid, kTeamThreads, smem, st>>>(a, tiles);
+}
+
+#define NFH_K_CASES(MACRO)                                                                          \
+  MACRO(1) MACRO(2) MACRO(3) MACRO(4) MACRO(5) MACRO(6) MACRO(7) MACRO(8) MACRO(9) MACRO(10) MACRO(11) \
+  MACRO(12) MACRO(13) MACRO(14) MACRO(15) MACRO(16)
+
 template <int G>
 static bool dispatch_k(int K, const FreqArgs &a, unsigned grid, cudaStream_t st) {
   switch (K) {
 #define NFH_CASE(k) case k: launch_warp_variant<G, k>(a, grid, st); return true;
-    NFH_CASE(1) NFH_CASE(2) NFH_CASE(3) NFH_CASE(4) NFH_CASE(5) NFH_CASE(6) NFH_CASE(7) NFH_CASE(8)
-    NFH_CASE(9) NFH_CASE(10) NFH_CASE(11) NFH_CASE(12) NFH_CASE(13) NFH_CASE(14) NFH_CASE(15) NFH_CASE(16)
+    NFH_K_CASES(NFH_CASE)
+#undef NFH_CASE
+    default: return false;
+  }
+}
+
+template <int W>
+static bool dispatch_team_k(int K, const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  switch (K) {
+#define NFH_CASE(k) case k: launch_team_variant<W, k>(a, grid, st); return true;
+    NFH_K_CASES(NFH_CASE)
 #undef NFH_CASE
     default: return false;
   }
 }
 
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  int G, K;
+  int G, K, W;
   if (pick_shape(a.n_ind, G, K)) {
     bool ok = false;
     switch (G) {
@@ -401,6 +554,14 @@ int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
       case 8: ok = dispatch_k<8>(K, a, grid, st); break;
       case 16: ok = dispatch_k<16>(K, a, grid, st); break;
       case 32: ok = dispatch_k<32>(K, a, grid, st); break;
+    }
+    if (ok) return 1;
+  } else if (pick_team_shape(a.n_ind, W, K)) {
+    bool ok = false;
+    switch (W) {
+      case 2: ok = dispatch_team_k<2>(K, a, grid, st); break;
+      case 4: ok = dispatch_team_k<4>(K, a, grid, st); break;
+      case 8: ok = dispatch_team_k<8>(K, a, grid, st); break;
     }
     if (ok) return 1;
   }

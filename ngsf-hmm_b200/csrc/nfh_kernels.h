@@ -29,8 +29,9 @@ struct EstepArgs {
   const double *dist;        // [n_ranks * site_block] Mb
   const double *indF, *alpha;
   const double *loge0_sum;   // [n_rows] sum over sites of log e0
-  ChunkProd *chunk_prod;     // [n_rows][n_tiles * 128]
-  double2 *fwd_carry, *bwd_carry;   // per chunk
+  double4 *chunk_prod;       // [n_rows][n_tiles * 128] direction-only chunk products
+  TileProd *tile_prod;       // [n_rows][n_tiles]
+  double2 *fwd_carry, *bwd_carry;   // per tile
   double *post;              // blocked like emis
   double *ind_lkl;
   int *status;

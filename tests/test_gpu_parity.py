@@ -125,8 +125,10 @@ def test_freq_update_matches_oracle(oracle, N, S, seed):
         _posterior_check(ctx.get_posterior(), marg2)
 
 
-def test_freq_update_streaming_variant_large_n(oracle):
-    N, S = 150, 300
+@pytest.mark.parametrize("N,S", [(150, 300), (600, 48), (1100, 40), (4200, 12)],
+                         ids=["warp-G32", "team-W2", "team-W4", "stream"])
+def test_freq_update_large_n_variants(oracle, N, S):
+    """More individuals than one lane group holds: 32-lane groups, teams of warps, and the streaming path."""
     d, ctx = _setup(N, S, 31, freq=(0.05, 0.5), indF=(0.0, 0.5))
     with ctx:
         gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.1, 0.1, 0.2)
