@@ -44,7 +44,9 @@ struct nfh_ctx {
   double2 *fwd_carry = nullptr, *bwd_carry = nullptr;
   LklGroup *groups = nullptr;
   double *neg_lkl = nullptr;
-  unsigned char *vit_work = nullptr;
+  unsigned char *vit_work = nullptr, *vit_maps = nullptr;
+  double4 *vit_tile_prod = nullptr;
+  int *vit_final = nullptr;
 
   // frequency side (all individuals, this rank's site block)
   double *gl[3] = {nullptr, nullptr, nullptr};
@@ -249,7 +251,7 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   void *dev[] = {ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
                  ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
-                 ctx->vit_work, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
+                 ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
                  ctx->status, ctx->d_stage};
   for (void *p : dev) if (p) cudaFree(p);
   if (ctx->n_ranks > 1) {
@@ -468,20 +470,34 @@ int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double
 int nfh_viterbi(nfh_ctx *ctx, char *path_out) {
   if (!ctx->e0_recv) return fail(ctx, NFH_ERR_ARG, "nfh_viterbi: call nfh_emission_refresh(ctx, 1) first");
   NFH_CUDA(cudaSetDevice(ctx->device));
-  const uint64_t n_pad8 = ((ctx->n_sites + 7) / 8) * 8;
-  if (!ctx->vit_work) NFH_CUDA(cudaMalloc((void **) &ctx->vit_work, ctx->n_loc * n_pad8));
+  const uint64_t stride = (uint64_t) ctx->n_tiles * kTile;            // whole tiles: bulk stores never run past a row
+  const size_t n_chunks = (size_t) ctx->n_tiles * kScanThreads;
+  if (!ctx->vit_work) {
+    NFH_CUDA(cudaMalloc((void **) &ctx->vit_work, ctx->n_loc * stride));
+    NFH_CUDA(cudaMalloc((void **) &ctx->vit_maps, ctx->n_loc * (n_chunks + 2 * (size_t) ctx->n_tiles)));
+    NFH_CUDA(cudaMalloc((void **) &ctx->vit_tile_prod, ctx->n_loc * ctx->n_tiles * sizeof(double4)));
+    NFH_CUDA(cudaMalloc((void **) &ctx->vit_final, ctx->n_loc * sizeof(int)));
+  }
   if (ctx->n_owned) {
     ViterbiArgs a;
     a.emis = ctx->emis_recv; a.e0 = ctx->e0_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
-    a.work = ctx->vit_work; a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
-    a.site_block = ctx->site_block;
+    a.work = ctx->vit_work; a.work_stride = stride;
+    a.chunk_prod = ctx->chunk_prod;                                    // E-step scratch, free between iterations
+    a.tile_prod = ctx->vit_tile_prod;
+    a.tile_score = ctx->fwd_carry;
+    a.chunk_map = ctx->vit_maps;
+    a.tile_map = ctx->vit_maps + ctx->n_loc * n_chunks;
+    a.tile_state = a.tile_map + ctx->n_loc * (size_t) ctx->n_tiles;
+    a.final_state = ctx->vit_final;
+    a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
+    a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
     {
-      FamilyScope fs(ctx, kFamViterbi, 1);
+      FamilyScope fs(ctx, kFamViterbi, 5);
       launch_viterbi(a, ctx->stream);
     }
     NFH_CUDA(cudaGetLastError());
     if (path_out)
-      NFH_CUDA(cudaMemcpy2DAsync(path_out, ctx->n_sites, ctx->vit_work, n_pad8, ctx->n_sites, ctx->n_owned,
+      NFH_CUDA(cudaMemcpy2DAsync(path_out, ctx->n_sites, ctx->vit_work, stride, ctx->n_sites, ctx->n_owned,
                                  cudaMemcpyDeviceToHost, ctx->stream));
   }
   NFH_CUDA(cudaStreamSynchronize(ctx->stream));

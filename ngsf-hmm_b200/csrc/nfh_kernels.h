@@ -12,10 +12,6 @@ struct TileProd {   // product of one tile's site matrices: [[a b][c d]] * 2^e *
   double a, b, c, d, e, l;
 };
 
-struct ChunkProd {   // product of one thread's 33 site matrices, same encoding as TileProd
-  double a, b, c, d, e, l;
-};
-
 struct LklGroup {   // objective requests of one individual sharing one read of its emissions
   int ind;
   int npts;
@@ -61,8 +57,13 @@ struct FreqArgs {
 
 struct ViterbiArgs {
   const double *emis, *e0, *dist, *indF, *alpha;
-  unsigned char *work;            // [n_rows][n_sites_pad] back-pointer bytes, overwritten with the path
-  uint64_t n_rows, n_rows_valid, n_sites, site_block;
+  unsigned char *work;            // [n_rows][work_stride] back-pointer bytes, overwritten with the path
+  double4 *chunk_prod, *tile_prod;   // (max,x) products: [n_rows][n_tiles*128], [n_rows][n_tiles]
+  double2 *tile_score;            // [n_rows][n_tiles] scores entering each tile
+  unsigned char *chunk_map, *tile_map, *tile_state;   // [n_rows][n_tiles*128], [n_rows][n_tiles] x2
+  int *final_state;               // [n_rows]
+  uint64_t n_rows, n_rows_valid, n_sites, site_block, work_stride;
+  uint32_t n_tiles;
 };
 
 void launch_estep(const EstepArgs &a, cudaStream_t st);

@@ -1,81 +1,350 @@
-// nfh_viterbi.cu - most probable IBD path.
+// nfh_viterbi.cu - most probable IBD path for all individuals, as chunked scans.
 //
-// Replaces viterbi() (shared/HMM.cpp:98-125) for all individuals.  Two quirks
-// of the reference are kept because they change the decoded tracts
-// (SURVEY.md finding 3):
+// Replaces viterbi() (shared/HMM.cpp:98-125).  Two quirks of the reference are
+// kept because they change the decoded tracts (SURVEY.md finding 3):
 //   * the score of state 0 is overwritten before state 1 of the same site is
 //     evaluated, so state 1 competes against the UPDATED state-0 score;
 //   * comparisons are strict (vmax < pval), so ties keep the k = 0 predecessor,
 //     and the final state is the first maximum (array_max_pos).
 //
-// The reference works in log space.  Here scores are kept in LINEAR space,
-// (max, x) instead of (max, +), rescaled by exact powers of two, which makes
-// the same decisions except where two candidates agree to ~1e-16 relative -
-// far inside the <1e-9 tie band the parity contract excludes.  No log/exp of
-// scores is needed, only c = exp(-alpha d) per site.
+// The reference works in log space.  Here scores live in LINEAR space, the
+// (max, x) semiring instead of (max, +), rescaled by exact powers of two, which
+// makes the same decisions except where two candidates agree to ~1e-16
+// relative - far inside the < 1e-9 tie band the parity contract excludes.
 //
-// v1: one thread per individual walks its sites (forward, then traceback).
+// With the in-place quirk one site is still a (max, x)-linear map of the score
+// pair (v0, v1).  Writing the transition as T = c A, A = I + kappa 1 q' (the
+// factored form of nfh_device.cuh), the update is
+//   new0 = c max(v0 A00, v1 A10) e0
+//   new1 = c max(new0 A01, v1 A11) e1          <- new0 already carries this site's c
+// so, unlike in the E-step, the scalar c does NOT cancel: after dropping the one
+// common factor c the state-1 candidate through state 0 keeps c A01 = (1-c) q1,
+// the true 0->1 transition probability t01:
+//   Q[0][0] = A00 e0              Q[0][1] = A00 e0 t01 e1
+//   Q[1][0] = A10 e0              Q[1][1] = max(A10 e0 t01, A11) e1
+// (e1 = e0 r).  The score pair
+// at any site is a chunked scan exactly like the E-step, and the traceback
+// path[s-1] = back[s][path[s]] is a scan of compositions of maps {0,1}->{0,1}.
+//
+//   viterbi_chunk_products : (max,x) product of each thread's 33 sites, and per tile
+//   viterbi_tile_scores    : per individual, scores at the start of every tile, final state
+//   viterbi_chunk_pointers : scores at chunk starts (in-CTA scan), 33 sites of back-pointer
+//                            pairs, composed map per chunk and per tile
+//   viterbi_tile_states    : per individual, state at the end of every tile (right to left)
+//   viterbi_chunk_trace    : state at the end of every chunk, then the 33-site traceback
 #include "nfh_device.cuh"
 #include "nfh_kernels.h"
 
 namespace nfh {
 
-__global__ void __launch_bounds__(64)
-viterbi_sequential(ViterbiArgs A) {
-  const uint64_t row = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= A.n_rows_valid) return;
+struct VitSmem {
+  alignas(128) double r[kTile];     // emission ratio e1/e0
+  alignas(128) double e0[kTile];
+  alignas(128) double d[kTile];
+  alignas(16) unsigned char bp[kTile];   // back-pointer pairs / path bytes of the tile
+  alignas(8) uint64_t bar;
+  double tab[64];
+};
+
+__device__ __forceinline__ int vit_valid_sites(uint64_t first_site, uint64_t n_sites) {
+  return first_site >= n_sites ? 0 : (int) min((uint64_t) kChunk, n_sites - first_site);
+}
+
+__device__ __forceinline__ void vit_stage(VitSmem &sm, const double *__restrict__ emis_tile,
+                                          const double *__restrict__ e0_tile, const double *__restrict__ dist_tile) {
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_fence_init();
+  }
+  load_exp_table(sm.tab);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&sm.bar, 3 * kTileBytes);
+    tma_load_1d(sm.r, emis_tile, kTileBytes, &sm.bar);
+    tma_load_1d(sm.e0, e0_tile, kTileBytes, &sm.bar);
+    tma_load_1d(sm.d, dist_tile, kTileBytes, &sm.bar);
+  }
+  mbar_wait(&sm.bar, 0);
+}
+
+// (max, x) product and helpers; entries are non-negative
+__device__ __forceinline__ M2 tropmul(const M2 &x, const M2 &y) {
+  M2 r;
+  r.a = fmax(x.a * y.a, x.b * y.c);
+  r.b = fmax(x.a * y.b, x.b * y.d);
+  r.c = fmax(x.c * y.a, x.d * y.c);
+  r.d = fmax(x.c * y.b, x.d * y.d);
+  return r;
+}
+
+struct SiteQ { double q00, q01, q10, q11; };
+
+// true 0->1 transition probability (1-c) q1 = kappa q1 / (1 + kappa); = q1 at chromosome starts
+__device__ __forceinline__ double trans01(double kap, double q1) { return kap * q1 * rcp_pos(1.0 + kap); }
+
+__device__ __forceinline__ SiteQ site_q(double kap, double q0, double q1, double e0, double r) {
+  const double k0 = kap * q0, k1 = kap * q1, e1 = e0 * r;
+  const double t01 = trans01(kap, q1);
+  SiteQ s;
+  s.q00 = (1.0 + k0) * e0;
+  s.q10 = k0 * e0;
+  s.q01 = s.q00 * t01 * e1;
+  s.q11 = fmax(s.q10 * t01, 1.0 + k1) * e1;
+  return s;
+}
+
+__device__ __forceinline__ void trop_apply(M2 &m, const SiteQ &s) {
+  const double a = fmax(m.a * s.q00, m.b * s.q10), b = fmax(m.a * s.q01, m.b * s.q11);
+  const double c = fmax(m.c * s.q00, m.d * s.q10), d = fmax(m.c * s.q01, m.d * s.q11);
+  m.a = a; m.b = b; m.c = c; m.d = d;
+}
+
+// ordered (max,x) product over the warp (lane 0 gets the total)
+__device__ __forceinline__ void warp_ordered_tropical(M2 &m) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const M2 o = shfl_down_m(m, off);
+    if ((lane & (2 * off - 1)) == 0) { m = tropmul(m, o); renorm(m); }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+viterbi_chunk_products(ViterbiArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VitSmem &sm = *reinterpret_cast<VitSmem *>(smem_raw);
+  const uint32_t tile = blockIdx.x, row = blockIdx.y;
+  const uint64_t tile_first = (uint64_t) tile * kTile;
+  const size_t tile_at = blocked_index(row, tile_first, A.n_rows, A.site_block);
+  vit_stage(sm, A.emis + tile_at, A.e0 + tile_at, A.dist + tile_first);
+
+  const int n_valid = vit_valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, A.n_sites);
   const double F = A.indF[row], al = A.alpha[row];
   const double q0 = 1.0 - F, q1 = F;
-  const uint64_t n_pad = ((A.n_sites + 7) / 8) * 8;
-  unsigned char *work = A.work + (size_t) row * n_pad;
+  const double *r = sm.r + threadIdx.x * kChunk, *e0 = sm.e0 + threadIdx.x * kChunk, *d = sm.d + threadIdx.x * kChunk;
 
-  double v0 = q0, v1 = q1;   // Vi_prob, linear
-  for (uint64_t s8 = 0; s8 < A.n_sites; s8 += 8) {
-    unsigned long long packed = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint64_t s = s8 + j;
-      if (s < A.n_sites) {
-        const size_t at = blocked_index(row, s, A.n_rows, A.site_block);
-        const double c = exp(-al * A.dist[s]);
-        const double e0 = A.e0[at];
-        const double e1 = e0 * A.emis[at];
-        const double g0 = (1.0 - c) * q0, g1 = (1.0 - c) * q1;
-        // l = 0: candidates from k = 0 (stay) and k = 1
-        double from0 = v0 * (g0 + c), from1 = v1 * g0;
-        unsigned bp0 = from1 > from0;
-        const double n0 = (bp0 ? from1 : from0) * e0;
-        // l = 1: k = 0 uses the score just written for state 0 (in-place quirk)
-        from0 = n0 * g1; from1 = v1 * (g1 + c);
-        unsigned bp1 = from1 > from0;
-        const double n1 = (bp1 ? from1 : from0) * e1;
-        v0 = n0; v1 = n1;
-        renorm2(v0, v1);
-        packed |= (unsigned long long) (bp0 | (bp1 << 1)) << (8 * j);
-      }
+  M2 m = identity2();
+#pragma unroll 3
+  for (int j = 0; j < kChunk; j++) {
+    if (j < n_valid) {
+      const double kap = site_kappa(al * d[j], sm.tab);
+      trop_apply(m, site_q(kap, q0, q1, e0[j], r[j]));
     }
-    *reinterpret_cast<unsigned long long *>(work + s8) = packed;
+    if (j % 6 == 5) renorm(m);
+  }
+  renorm(m);
+  A.chunk_prod[((size_t) row * A.n_tiles + tile) * kScanThreads + threadIdx.x] = make_double4(m.a, m.b, m.c, m.d);
+
+  __shared__ M2 sm_m[kScanThreads / 32];
+  warp_ordered_tropical(m);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sm_m[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    M2 acc = sm_m[0];
+#pragma unroll
+    for (int w = 1; w < kScanThreads / 32; w++) { acc = tropmul(acc, sm_m[w]); renorm(acc); }
+    A.tile_prod[(size_t) row * A.n_tiles + tile] = make_double4(acc.a, acc.b, acc.c, acc.d);
+  }
+}
+
+// One warp per individual: scores entering every tile (32 tiles per step, warp scan), final state.
+__global__ void __launch_bounds__(128)
+viterbi_tile_scores(ViterbiArgs A) {
+  const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= A.n_rows_valid) return;
+  const double F = A.indF[row];
+  double v0 = 1.0 - F, v1 = F;                                  // Vi_prob = q, linear
+  const double4 *tp = A.tile_prod + (size_t) row * A.n_tiles;
+  double2 *score = A.tile_score + (size_t) row * A.n_tiles;
+  for (uint32_t g = 0; g < (A.n_tiles + 31) / 32; g++) {
+    const uint32_t t = g * 32 + lane;
+    M2 m = identity2();
+    if (t < A.n_tiles) { const double4 p = tp[t]; m.a = p.x; m.b = p.y; m.c = p.z; m.d = p.w; }
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const M2 o = shfl_up_m(m, off);
+      if (lane >= off) { m = tropmul(o, m); renorm(m); }
+    }
+    const M2 before = shfl_up_m(m, 1);
+    double c0 = v0, c1 = v1;
+    if (lane > 0) { c0 = fmax(v0 * before.a, v1 * before.c); c1 = fmax(v0 * before.b, v1 * before.d); renorm2(c0, c1); }
+    if (t < A.n_tiles) score[t] = make_double2(c0, c1);
+    M2 tot;
+    tot.a = __shfl_sync(kFull, m.a, 31); tot.b = __shfl_sync(kFull, m.b, 31);
+    tot.c = __shfl_sync(kFull, m.c, 31); tot.d = __shfl_sync(kFull, m.d, 31);
+    const double y0 = fmax(v0 * tot.a, v1 * tot.c), y1 = fmax(v0 * tot.b, v1 * tot.d);
+    v0 = y0; v1 = y1;
+    renorm2(v0, v1);
+  }
+  if (lane == 0) A.final_state[row] = v1 > v0 ? 1 : 0;           // array_max_pos: first maximum
+}
+
+// maps {0,1} -> {0,1} as 2 bits: bit x = image of x.  compose(f, g)(x) = f(g(x)).
+__device__ __forceinline__ unsigned map_compose(unsigned f, unsigned g) {
+  return ((f >> (g & 1u)) & 1u) | (((f >> ((g >> 1) & 1u)) & 1u) << 1);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+viterbi_chunk_pointers(ViterbiArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VitSmem &sm = *reinterpret_cast<VitSmem *>(smem_raw);
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ M2 warp_tot[kWarps];
+  __shared__ unsigned warp_map[kWarps];
+  const uint32_t tile = blockIdx.x, row = blockIdx.y;
+  const uint64_t tile_first = (uint64_t) tile * kTile;
+  const size_t tile_at = blocked_index(row, tile_first, A.n_rows, A.site_block);
+  vit_stage(sm, A.emis + tile_at, A.e0 + tile_at, A.dist + tile_first);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_valid = vit_valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, A.n_sites);
+  const double F = A.indF[row], al = A.alpha[row];
+  const double q0 = 1.0 - F, q1 = F;
+
+  // scores entering my chunk: tile score x products of the chunks before me
+  const double4 mine4 = A.chunk_prod[((size_t) row * A.n_tiles + tile) * kScanThreads + threadIdx.x];
+  M2 pre; pre.a = mine4.x; pre.b = mine4.y; pre.c = mine4.z; pre.d = mine4.w;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const M2 o = shfl_up_m(pre, off);
+    if (lane >= off) { pre = tropmul(o, pre); renorm(pre); }
+  }
+  if (lane == 31) warp_tot[warp] = pre;
+  __syncthreads();
+  const double2 ts = A.tile_score[(size_t) row * A.n_tiles + tile];
+  double v0 = ts.x, v1 = ts.y;
+  for (int w = 0; w < warp; w++) {
+    const M2 p = warp_tot[w];
+    const double y0 = fmax(v0 * p.a, v1 * p.c), y1 = fmax(v0 * p.b, v1 * p.d);
+    v0 = y0; v1 = y1;
+    renorm2(v0, v1);
+  }
+  const M2 before = shfl_up_m(pre, 1);
+  if (lane > 0) {
+    const double y0 = fmax(v0 * before.a, v1 * before.c), y1 = fmax(v0 * before.b, v1 * before.d);
+    v0 = y0; v1 = y1;
+    renorm2(v0, v1);
   }
 
-  // traceback: path[S-1] = first max; path[s-1] = back[s][path[s]]
-  unsigned state = v1 > v0 ? 1u : 0u;
-  for (uint64_t s8 = n_pad; s8 >= 8; s8 -= 8) {
-    unsigned long long packed = *reinterpret_cast<unsigned long long *>(work + s8 - 8);
-    unsigned long long out = 0;
-#pragma unroll
-    for (int j = 7; j >= 0; j--) {
-      if (s8 - 8 + j < A.n_sites) {
-        out |= (unsigned long long) state << (8 * j);
-        const unsigned bits = (unsigned) (packed >> (8 * j)) & 3u;
-        state = (bits >> state) & 1u;
-      }
+  // my 33 sites: back-pointer pair per site, composed map of the chunk
+  const double *r = sm.r + threadIdx.x * kChunk, *e0 = sm.e0 + threadIdx.x * kChunk, *d = sm.d + threadIdx.x * kChunk;
+  unsigned char *bp = sm.bp + threadIdx.x * kChunk;
+  unsigned chunk_map = 2u;                                       // identity: 0->0, 1->1
+#pragma unroll 3
+  for (int j = 0; j < kChunk; j++) {
+    unsigned bits = 2u;                                          // padding sites: identity
+    if (j < n_valid) {
+      const double kap = site_kappa(al * d[j], sm.tab);
+      const double k0 = kap * q0, k1 = kap * q1, e1 = e0[j] * r[j];
+      // l = 0: candidates from k = 0 (stay) and k = 1
+      double from0 = v0 * (1.0 + k0), from1 = v1 * k0;
+      const unsigned bp0 = from1 > from0;
+      const double n0 = (bp0 ? from1 : from0) * e0[j];
+      // l = 1: k = 0 uses the score just written for state 0 (in-place quirk), which already
+      // carries this site's factor c: c kappa q1 = (1-c) q1
+      from0 = n0 * trans01(kap, q1); from1 = v1 * (1.0 + k1);
+      const unsigned bp1 = from1 > from0;
+      const double n1 = (bp1 ? from1 : from0) * e1;
+      v0 = n0; v1 = n1;
+      if (j % 4 == 3) renorm2(v0, v1);
+      bits = bp0 | (bp1 << 1);
     }
-    *reinterpret_cast<unsigned long long *>(work + s8 - 8) = out;
+    bp[j] = (unsigned char) bits;
+    // path[s-1] = bits_s[path[s]]: the chunk map sends the state at the chunk's last site back
+    // to the state before its first site, i.e. f_first o ... o f_last
+    chunk_map = map_compose(chunk_map, bits);
+  }
+  A.chunk_map[((size_t) row * A.n_tiles + tile) * kScanThreads + threadIdx.x] = (unsigned char) chunk_map;
+
+  // tile map = map_0 o map_1 o ... o map_127 (ordered reduction)
+  unsigned m = chunk_map;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned o = __shfl_down_sync(kFull, m, off);
+    if ((lane & (2 * off - 1)) == 0) m = map_compose(m, o);
+  }
+  if (lane == 0) warp_map[warp] = m;
+  fence_async_shared();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned acc = warp_map[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; w++) acc = map_compose(acc, warp_map[w]);
+    A.tile_map[(size_t) row * A.n_tiles + tile] = (unsigned char) acc;
+    tma_store_1d(A.work + (size_t) row * A.work_stride + tile_first, sm.bp, kTile);
+    tma_store_wait_read();
+  }
+}
+
+// One thread per individual: state at the end of every tile, right to left.
+__global__ void viterbi_tile_states(ViterbiArgs A) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= A.n_rows_valid) return;
+  unsigned state = A.final_state[row];
+  const unsigned char *tm = A.tile_map + (size_t) row * A.n_tiles;
+  unsigned char *ts = A.tile_state + (size_t) row * A.n_tiles;
+  for (uint32_t t = A.n_tiles; t-- > 0;) {
+    ts[t] = (unsigned char) state;                               // state at the last site of tile t
+    state = (tm[t] >> state) & 1u;                               // state at the last site of tile t-1
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+viterbi_chunk_trace(ViterbiArgs A) {
+  __shared__ alignas(16) unsigned char tile_bytes[kTile];
+  __shared__ unsigned char maps[kScanThreads];
+  __shared__ unsigned char end_state[kScanThreads];
+  __shared__ alignas(8) uint64_t bar;
+  const uint32_t tile = blockIdx.x, row = blockIdx.y;
+  const uint64_t tile_first = (uint64_t) tile * kTile;
+  unsigned char *gl_tile = A.work + (size_t) row * A.work_stride + tile_first;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  maps[threadIdx.x] = A.chunk_map[((size_t) row * A.n_tiles + tile) * kScanThreads + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, kTile);
+    tma_load_1d(tile_bytes, gl_tile, kTile, &bar);
+    // state at the last site of every chunk, right to left (128 two-bit maps: one thread is plenty)
+    unsigned state = A.tile_state[(size_t) row * A.n_tiles + tile];
+    for (int c = kScanThreads - 1; c >= 0; c--) {
+      end_state[c] = (unsigned char) state;
+      state = (maps[c] >> state) & 1u;
+    }
+  }
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  const int n_valid = vit_valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, A.n_sites);
+  unsigned char *b = tile_bytes + threadIdx.x * kChunk;
+  unsigned state = end_state[threadIdx.x];
+#pragma unroll 3
+  for (int j = kChunk - 1; j >= 0; j--) {
+    const unsigned bits = b[j];
+    b[j] = (unsigned char) (j < n_valid ? state : 0u);
+    state = (bits >> state) & 1u;
+  }
+  fence_async_shared();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_store_1d(gl_tile, tile_bytes, kTile);
+    tma_store_wait_read();
   }
 }
 
 void launch_viterbi(const ViterbiArgs &a, cudaStream_t st) {
-  viterbi_sequential<<<(unsigned) ((a.n_rows_valid + 63) / 64), 64, 0, st>>>(a);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(viterbi_chunk_products, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
+    cudaFuncSetAttribute(viterbi_chunk_pointers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
+    attr_done = true;
+  }
+  dim3 grid(a.n_tiles, (unsigned) a.n_rows_valid);
+  viterbi_chunk_products<<<grid, kScanThreads, sizeof(VitSmem), st>>>(a);
+  viterbi_tile_scores<<<(unsigned) ((a.n_rows_valid + 3) / 4), 128, 0, st>>>(a);
+  viterbi_chunk_pointers<<<grid, kScanThreads, sizeof(VitSmem), st>>>(a);
+  viterbi_tile_states<<<(unsigned) ((a.n_rows_valid + 63) / 64), 64, 0, st>>>(a);
+  viterbi_chunk_trace<<<grid, kScanThreads, 0, st>>>(a);
 }
 
 }  // namespace nfh
