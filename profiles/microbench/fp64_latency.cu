@@ -57,6 +57,49 @@ double run3(int warps_per_sm, int sms, double *sink) {
   return (double) sms * ctas_per_sm * threads * iters * ILP * 2.0 / (ms * 1e-3);
 }
 
+// K independent "individuals": one MUFU.RCP64H seed + NF dependent-ish DFMAs each, as in the
+// frequency kernel's inner loop.  Reports DFMA/s to see what the MUFU costs the FP64 pipe.
+template <int K, int NF, bool MUFU>
+__global__ void rcp_mix(double *sink, int iters) {
+  double x[K], acc[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) { x[i] = 1.0 + threadIdx.x * 1e-3 + i; acc[i] = 0; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      double y;
+      if (MUFU) asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x[i]));
+      else y = x[i] * 0.5;
+#pragma unroll
+      for (int f = 0; f < NF; f++) y = fma(y, x[i], 1e-9);
+      acc[i] += y;
+      x[i] = fma(x[i], 0.999999, 1e-7);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < K; i++) s += acc[i];
+  if (s == 12345.678) sink[0] = s;
+}
+
+template <int K, int NF, bool MUFU>
+double run_mix(int warps_per_sm, int sms, double *sink) {
+  const int iters = 1 << 11;
+  int threads = 32 * (warps_per_sm >= 8 ? 8 : warps_per_sm);
+  int ctas_per_sm = (warps_per_sm * 32) / threads;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  rcp_mix<K, NF, MUFU><<<sms * ctas_per_sm, threads>>>(sink, iters);
+  cudaEventRecord(e0);
+  rcp_mix<K, NF, MUFU><<<sms * ctas_per_sm, threads>>>(sink, iters);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  // FP64 instructions per individual: NF fma + 1 add + 1 fma (+1 mul when no MUFU)
+  return (double) sms * ctas_per_sm * threads * iters * K * (NF + 2 + (MUFU ? 0 : 1)) / (ms * 1e-3);
+}
+
 __global__ void latency_dfma(long long *out, double *sink, int iters) {
   double x = threadIdx.x * 1e-9;
   const double m = 0.999999999, c = 1e-12;
@@ -119,6 +162,12 @@ int main() {
   printf("3-distinct-operand DFMA/s (1e12), ILP 8: warps/SM 8: %.2f  16: %.2f  32: %.2f  64: %.2f\n",
          run3<8>(8, sms, sink) / 1e12, run3<8>(16, sms, sink) / 1e12, run3<8>(32, sms, sink) / 1e12,
          run3<8>(64, sms, sink) / 1e12);
+  printf("FP64 instr/s (1e12) with 1 MUFU.RCP64H per 9 FP64 (K=13 chains), 8 warps/SM: %.2f ; 16 warps/SM: %.2f\n",
+         run_mix<13, 7, true>(8, sms, sink) / 1e12, run_mix<13, 7, true>(16, sms, sink) / 1e12);
+  printf("same without the MUFU (DMUL instead), 8 warps/SM: %.2f ; 16 warps/SM: %.2f\n",
+         run_mix<13, 7, false>(8, sms, sink) / 1e12, run_mix<13, 7, false>(16, sms, sink) / 1e12);
+  printf("1 MUFU per 18 FP64, 8 warps/SM: %.2f ; 1 MUFU per 36 FP64: %.2f\n",
+         run_mix<13, 16, true>(8, sms, sink) / 1e12, run_mix<13, 34, true>(8, sms, sink) / 1e12);
   long long h;
   latency_dfma<<<1, 32>>>(out, sink, 1000);
   latency_dfma<<<1, 32>>>(out, sink, 1000);
