@@ -444,6 +444,12 @@ int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double
     g->out[g->npts] = (int) q;
     g->npts++;
   }
+  for (uint32_t k = 0; k < n_groups; k++) {
+    LklGroup &gg = ctx->h_groups[k];
+    gg.n_same = 1;
+    while (gg.n_same < gg.npts && gg.alpha[gg.n_same] == gg.alpha[0]) gg.n_same++;
+    gg.pad_ = 0;
+  }
   if (n_groups == 0) return NFH_OK;
   NFH_CUDA(cudaMemcpyAsync(ctx->groups, ctx->h_groups, n_groups * sizeof(LklGroup), cudaMemcpyHostToDevice,
                            ctx->stream));

@@ -74,16 +74,26 @@ estep_chunk_products(const double *__restrict__ emis, const double *__restrict__
   const double *r = sm.r + threadIdx.x * kChunk;
   const double *d = sm.d + threadIdx.x * kChunk;
 
+  // Straight-line bodies of kBody sites (no branches inside: padding sites are turned into the
+  // identity by selecting r = 1; their distance is 0, so kappa = 0 and the scale term is 0).
   M2 m = identity2();
   int e = 0;
   double ls = 0.0;
+  constexpr int kBody = 6;
+#pragma unroll 1
+  for (int j0 = 0; j0 + kBody <= kChunk; j0 += kBody) {
 #pragma unroll
-  for (int j = 0; j < kChunk; j++) {
-    if (j < n_valid) {
+    for (int i = 0; i < kBody; i++) {
+      const int j = j0 + i;
       const double kap = site_kappa(al * d[j], sm.tab, ls);
-      apply_site(m, kap * q0, kap * q1, r[j]);
+      apply_site(m, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
     }
-    if (j % 6 == 5) e += renorm(m);
+    e += renorm(m);
+  }
+#pragma unroll
+  for (int j = (kChunk / kBody) * kBody; j < kChunk; j++) {
+    const double kap = site_kappa(al * d[j], sm.tab, ls);
+    apply_site(m, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
   }
   e += renorm(m);
   // per-chunk product (direction only: the apply kernel is scale free)
@@ -287,9 +297,9 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
 #pragma unroll
     for (int i = 0; i < kSub; i++) {
       const int j = sb * kSub + i;
-      const double kap = site_kappa(al * d[j], sm.tab);
+      const double kap = site_kappa(al * d[j], sm.tab);     // padding: d = 0 -> kappa = 0
       d[j] = kap;
-      if (j < n_valid) forward_site(a0, a1, kap * q0, kap * q1, r[j]);
+      forward_site(a0, a1, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
       if (i == kSub / 2) renorm2(a0, a1);
     }
   }
@@ -306,10 +316,10 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
 #pragma unroll
     for (int i = 0; i < kSub; i++) {
       const int j = sb * kSub + i;
-      rr[i] = r[j];
+      rr[i] = j < n_valid ? r[j] : 1.0;
       const double kap = d[j];
       k0[i] = kap * q0; k1[i] = kap * q1;
-      if (j < n_valid) forward_site(a0, a1, k0[i], k1[i], rr[i]);
+      forward_site(a0, a1, k0[i], k1[i], rr[i]);
       if (i == kSub / 2) renorm2(a0, a1);
       f0[i] = a0; f1[i] = a1;
     }
@@ -319,16 +329,12 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
       const double num = f1[i] * b1;
       const double den = fma(f0[i], b0, num);
       double p = num * rcp_pos(den);
-      if (j < n_valid) {
-        bad |= (p != p);
-        p = (p < kEps) ? 0.0 : p;              // check_interv, gen_func.cpp:59-66
-        p = (p > 1.0 - kEps) ? 1.0 : p;
-        backward_site(b0, b1, k0[i], k1[i], rr[i]);
-        if (i == kSub / 2) renorm2(b0, b1);
-      } else {
-        p = 0.0;
-      }
-      r[j] = p;
+      bad |= (p != p);
+      p = (p < kEps) ? 0.0 : p;                // check_interv, gen_func.cpp:59-66
+      p = (p > 1.0 - kEps) ? 1.0 : p;
+      backward_site(b0, b1, k0[i], k1[i], rr[i]);   // identity on padding sites (kappa = 0, r = 1)
+      if (i == kSub / 2) renorm2(b0, b1);
+      r[j] = j < n_valid ? p : 0.0;
     }
     renorm2(b0, b1);
   }
@@ -354,46 +360,55 @@ struct LklSmem {
   double l[kMaxPoints][kScanThreads / 32];
 };
 
-template <int NP>
+// NS leading points share alpha (one kappa per site for all of them); the next NA points each have
+// their own.  The layout is fixed per group, so the whole body is straight-line code.
+template <int NS, int NA>
 __device__ __forceinline__ void lkl_tile_body(const LklGroup &g, LklSmem &sm, int n_valid,
                                               TileProd *__restrict__ out_row, uint32_t n_tiles, uint32_t tile) {
+  constexpr int NP = NS + NA;
+  constexpr int kBody = 6;
   const double *r = sm.t.r + threadIdx.x * kChunk;
   const double *d = sm.t.d + threadIdx.x * kChunk;
   M2 m[NP];
   int e[NP];
-  double ls[NP];
-  bool fresh[NP];   // does point p need its own kappa, or does it share alpha with p-1
+  double ls[1 + NA];          // scale sums: one for the shared alpha, one per extra alpha
+  double q1[NP], q0[NP];
 #pragma unroll
-  for (int p = 0; p < NP; p++) {
-    m[p] = identity2(); e[p] = 0; ls[p] = 0.0;
-    fresh[p] = (p == 0) || (g.alpha[p] != g.alpha[p - 1]);
-  }
-#pragma unroll 3
-  for (int j = 0; j < kChunk; j++) {
-    const double dj = d[j], rj = r[j];
-    const bool live = j < n_valid;
-    double kap = 0.0, l = 0.0;
+  for (int p = 0; p < NP; p++) { m[p] = identity2(); e[p] = 0; q1[p] = g.F[p]; q0[p] = 1.0 - g.F[p]; }
 #pragma unroll
-    for (int p = 0; p < NP; p++) {
-      if (fresh[p]) { l = 0.0; kap = site_kappa(g.alpha[p] * dj, sm.t.tab, l); }
-      if (live) {
-        apply_site(m[p], kap * (1.0 - g.F[p]), kap * g.F[p], rj);
-        ls[p] += l;
-      }
+  for (int a = 0; a <= NA; a++) ls[a] = 0.0;
+
+  auto site = [&](int j) {
+    const double dj = d[j];
+    const double rj = j < n_valid ? r[j] : 1.0;      // padding: identity (d = 0 -> kappa = 0)
+    const double ks = site_kappa(g.alpha[0] * dj, sm.t.tab, ls[0]);
+#pragma unroll
+    for (int p = 0; p < NS; p++) apply_site(m[p], ks * q0[p], ks * q1[p], rj);
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const double ka = site_kappa(g.alpha[NS + a] * dj, sm.t.tab, ls[1 + a]);
+      apply_site(m[NS + a], ka * q0[NS + a], ka * q1[NS + a], rj);
     }
-    if (j % 6 == 5) {
+  };
+#pragma unroll 1
+  for (int j0 = 0; j0 + kBody <= kChunk; j0 += kBody) {
 #pragma unroll
-      for (int p = 0; p < NP; p++) e[p] += renorm(m[p]);
-    }
+    for (int i = 0; i < kBody; i++) site(j0 + i);
+#pragma unroll
+    for (int p = 0; p < NP; p++) e[p] += renorm(m[p]);
   }
+#pragma unroll
+  for (int j = (kChunk / kBody) * kBody; j < kChunk; j++) site(j);
+
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     e[p] += renorm(m[p]);
     warp_ordered_product(m[p], e[p]);
+    double l = ls[p < NS ? 0 : 1 + (p - NS)];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ls[p] += __shfl_down_sync(kFull, ls[p], off);
-    if (lane == 0) { sm.m[p][warp] = m[p]; sm.e[p][warp] = e[p]; sm.l[p][warp] = ls[p]; }
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_down_sync(kFull, l, off);
+    if (lane == 0) { sm.m[p][warp] = m[p]; sm.e[p][warp] = e[p]; sm.l[p][warp] = l; }
   }
   __syncthreads();
   if ((int) threadIdx.x < NP) {
@@ -424,13 +439,17 @@ lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ di
   stage_tile(sm.t, emis + blocked_index((uint64_t) g.ind, tile_first, n_rows, site_block), dist + tile_first);
   const int n_valid = valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, n_sites);
   TileProd *out_row = tile_prod + (size_t) grp * kMaxPoints * n_tiles;
-  switch (g.npts) {   // uniform per CTA
-    case 1: lkl_tile_body<1>(g, sm, n_valid, out_row, n_tiles, tile); break;
-    case 2: lkl_tile_body<2>(g, sm, n_valid, out_row, n_tiles, tile); break;
-    case 3: lkl_tile_body<3>(g, sm, n_valid, out_row, n_tiles, tile); break;
-    case 4: lkl_tile_body<4>(g, sm, n_valid, out_row, n_tiles, tile); break;
-    default: lkl_tile_body<5>(g, sm, n_valid, out_row, n_tiles, tile); break;
+  // uniform per CTA: (points sharing alpha with point 0, further points)
+#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_body<ns, na>(g, sm, n_valid, out_row, n_tiles, tile); break;
+  switch (g.n_same * 8 + (g.npts - g.n_same)) {
+    NFH_LKL(1, 0) NFH_LKL(1, 1) NFH_LKL(1, 2) NFH_LKL(1, 3) NFH_LKL(1, 4)
+    NFH_LKL(2, 0) NFH_LKL(2, 1) NFH_LKL(2, 2) NFH_LKL(2, 3)
+    NFH_LKL(3, 0) NFH_LKL(3, 1) NFH_LKL(3, 2)
+    NFH_LKL(4, 0) NFH_LKL(4, 1)
+    NFH_LKL(5, 0)
+    default: break;
   }
+#undef NFH_LKL
 }
 
 // One warp per (group, point): lanes take contiguous runs of tile products,

@@ -15,6 +15,8 @@ struct TileProd {   // product of one tile's site matrices: [[a b][c d]] * 2^e *
 struct LklGroup {   // objective requests of one individual sharing one read of its emissions
   int ind;
   int npts;
+  int n_same;    // leading points whose alpha equals alpha[0] (they share one kappa per site)
+  int pad_;
   double F[kMaxPoints];
   double alpha[kMaxPoints];
   int out[kMaxPoints];
