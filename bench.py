@@ -200,6 +200,13 @@ def main():
     torch.cuda.empty_cache()
 
     runner = nfh.EmRank(ctx, freq_est=1)
+    exchange = "none (1 rank)"
+    if world > 1:
+        if os.environ.get("NFH_PEER_DIRECT", "1") != "0":
+            runner.enable_peer_direct()
+            exchange = "fused: kernels store into peer windows over NVLink (CUDA IPC)"
+        else:
+            exchange = "NCCL all-to-all"
     n_own = ctx.n_ind_owned
 
     def reset_state():
@@ -293,7 +300,8 @@ def main():
                                    f"--freq_est 1, start --freq 0.1 --indF 0.1,0.2; {N_total} individuals total",
                        "step": "one EM iteration = E-step + lockstep BFGS(F,alpha) + freq EM + emission refresh",
                        "l2": "inputs per step (GL+emission+posterior = 4.0 GB per GPU) exceed the 126 MB L2",
-                       "parallelism": f"individuals sharded x{world}, sites sharded x{world} for the freq stage"},
+                       "parallelism": f"individuals sharded x{world}, sites sharded x{world} for the freq stage",
+                       "exchange": exchange},
             "roofline": roofs[dominant], "roofline_estep": roof_estep, "roofline_freq": roof_freq,
             "roofline_lkl_batch": roof_lkl,
             "kernel_ms_per_step": per_step,

@@ -143,6 +143,19 @@ int nfh_geno_posterior(nfh_ctx *ctx, const char *path_all, double *geno_out);
  * all-reduce.  bytes_per_peer = bytes / n_ranks for the all-to-all windows. */
 int nfh_exchange_window(nfh_ctx *ctx, int window, void **dev_ptr, uint64_t *bytes, uint64_t *bytes_per_peer);
 
+/* Fused exchange over NVLink peer memory (one process per GPU, same node).  Each rank exports CUDA IPC
+ * handles (64 bytes) of its two receive windows, the host plumbing all-gathers them, every rank imports
+ * the handles of all ranks (its own included), then nfh_peer_direct(ctx, 1) makes
+ *   - nfh_estep write every posterior tile straight into the frequency-side window of the rank that
+ *     owns the tile's site block, and
+ *   - nfh_freq_update / nfh_emission_refresh write every emission ratio straight into the
+ *     recursion-side window of the rank that owns the individual,
+ * so no all-to-all is needed; the caller only has to order the stages across ranks (a 1-element
+ * all-reduce on nfh_stream() before nfh_freq_update, and the all-reduce of NFH_WIN_LOGE0_SUM after it). */
+int nfh_peer_export(nfh_ctx *ctx, int window, unsigned char handle[64]);
+int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char handle[64]);
+int nfh_peer_direct(nfh_ctx *ctx, int enable);
+
 /* Block until everything queued by this context has finished; returns the
  * sticky device status (NaN / FwBw flags raised by kernels). */
 int nfh_sync(nfh_ctx *ctx);

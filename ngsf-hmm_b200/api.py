@@ -27,7 +27,7 @@ EXPORTS = [
     "nfh_n_ind_local", "nfh_n_ind_owned", "nfh_ind_begin", "nfh_site_block", "nfh_site_begin", "nfh_sites_owned",
     "nfh_upload_gl", "nfh_upload_pos_dist", "nfh_set_freq", "nfh_get_freq", "nfh_set_ind_params",
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
-    "nfh_geno_posterior", "nfh_exchange_window", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
+    "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
     "nfh_timing_read",
 ]
 
@@ -89,6 +89,9 @@ def load_library():
     L.nfh_geno_posterior.restype = cint; L.nfh_geno_posterior.argtypes = [_vp, _vp, _dp]
     L.nfh_exchange_window.restype = cint
     L.nfh_exchange_window.argtypes = [_vp, cint, C.POINTER(_vp), C.POINTER(u64), C.POINTER(u64)]
+    L.nfh_peer_export.restype = cint; L.nfh_peer_export.argtypes = [_vp, cint, C.c_char_p]
+    L.nfh_peer_import.restype = cint; L.nfh_peer_import.argtypes = [_vp, cint, cint, C.c_char_p]
+    L.nfh_peer_direct.restype = cint; L.nfh_peer_direct.argtypes = [_vp, cint]
     L.nfh_sync.restype = cint; L.nfh_sync.argtypes = [_vp]
     L.nfh_stream.restype = _vp; L.nfh_stream.argtypes = [_vp]
     L.nfh_probe_fp64.restype = cint; L.nfh_probe_fp64.argtypes = [_vp, _dp]
@@ -231,6 +234,17 @@ class Context:
 
     def sync(self):
         self._chk(self.L.nfh_sync(self.h))
+
+    def peer_export(self, which):
+        buf = C.create_string_buffer(64)
+        self._chk(self.L.nfh_peer_export(self.h, which, buf))
+        return buf.raw
+
+    def peer_import(self, which, peer_rank, handle):
+        self._chk(self.L.nfh_peer_import(self.h, which, peer_rank, handle))
+
+    def peer_direct(self, enable=True):
+        self._chk(self.L.nfh_peer_direct(self.h, int(enable)))
 
     @property
     def stream(self):

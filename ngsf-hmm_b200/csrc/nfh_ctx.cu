@@ -54,6 +54,10 @@ struct nfh_ctx {
   double *loge0_part = nullptr, *loge0_sum = nullptr;
   unsigned loge0_rows = 0;
 
+  // peer windows (CUDA IPC), see nfh_peer_*
+  double *peer_post[kMaxRanks] = {nullptr}, *peer_emis[kMaxRanks] = {nullptr};
+  bool peer_direct = false;
+
   int *status = nullptr;
   // pinned host scratch
   double *h_small = nullptr;       // 8 * max(n_loc, 16) doubles + requests
@@ -254,6 +258,11 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
                  ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
                  ctx->status, ctx->d_stage};
   for (void *p : dev) if (p) cudaFree(p);
+  for (int r = 0; r < kMaxRanks; r++) {
+    if (r == ctx->rank) continue;
+    if (ctx->peer_post[r]) cudaIpcCloseMemHandle(ctx->peer_post[r]);
+    if (ctx->peer_emis[r]) cudaIpcCloseMemHandle(ctx->peer_emis[r]);
+  }
   if (ctx->n_ranks > 1) {
     if (ctx->post_recv) cudaFree(ctx->post_recv);
     if (ctx->emis_send) cudaFree(ctx->emis_send);
@@ -354,6 +363,9 @@ static int run_freq_family(nfh_ctx *ctx, int family, int update, bool zero_post,
   a.post = zero_post ? nullptr : ctx->post_recv;
   a.freq = ctx->freq; a.emis = ctx->emis_send; a.e0 = with_e0 ? ctx->e0_send : nullptr;
   a.loge0_part = ctx->loge0_part;
+  a.emis_peers.direct = ctx->peer_direct ? 1 : 0;
+  a.emis_peers.rank = ctx->rank; a.emis_peers.n_loc = ctx->n_loc;
+  for (int r = 0; r < kMaxRanks; r++) a.emis_peers.base[r] = ctx->peer_emis[r];
   a.n_ind = ctx->n_ind_total; a.n_ind_pad = ctx->n_ind_pad;
   a.site_block = ctx->site_block; a.sites_owned = ctx->sites_owned;
   a.update_freq = update;
@@ -400,6 +412,9 @@ int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out) {
     a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
     a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
     a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
+    a.post_peers.direct = ctx->peer_direct ? 1 : 0;
+    a.post_peers.rank = ctx->rank; a.post_peers.n_loc = ctx->n_loc;
+    for (int r = 0; r < kMaxRanks; r++) a.post_peers.base[r] = ctx->peer_post[r];
     a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
     a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
     {
@@ -562,6 +577,45 @@ int nfh_exchange_window(nfh_ctx *ctx, int window, void **dev_ptr, uint64_t *byte
   if (dev_ptr) *dev_ptr = p;
   if (bytes) *bytes = b;
   if (bytes_per_peer) *bytes_per_peer = b / ctx->n_ranks;
+  return NFH_OK;
+}
+
+int nfh_peer_export(nfh_ctx *ctx, int window, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  void *p = window == NFH_WIN_POST_RECV ? (void *) ctx->post_recv : window == NFH_WIN_EMIS_RECV ? (void *) ctx->emis_recv : nullptr;
+  if (!p) return fail(ctx, NFH_ERR_ARG, "nfh_peer_export: only POST_RECV and EMIS_RECV can be exported");
+  cudaIpcMemHandle_t h;
+  NFH_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle, &h, 64);
+  return NFH_OK;
+}
+
+int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char handle[64]) {
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  if (peer_rank < 0 || peer_rank >= ctx->n_ranks || ctx->n_ranks > kMaxRanks)
+    return fail(ctx, NFH_ERR_ARG, "nfh_peer_import: bad rank");
+  double **slot = window == NFH_WIN_POST_RECV ? ctx->peer_post : window == NFH_WIN_EMIS_RECV ? ctx->peer_emis : nullptr;
+  if (!slot) return fail(ctx, NFH_ERR_ARG, "nfh_peer_import: only POST_RECV and EMIS_RECV can be imported");
+  if (peer_rank == ctx->rank) {
+    slot[peer_rank] = window == NFH_WIN_POST_RECV ? ctx->post_recv : ctx->emis_recv;
+    return NFH_OK;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void *p = nullptr;
+  NFH_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  slot[peer_rank] = (double *) p;
+  return NFH_OK;
+}
+
+int nfh_peer_direct(nfh_ctx *ctx, int enable) {
+  if (enable) {
+    for (int r = 0; r < ctx->n_ranks; r++)
+      if (!ctx->peer_post[r] || !ctx->peer_emis[r])
+        return fail(ctx, NFH_ERR_ARG, "nfh_peer_direct: import the POST_RECV and EMIS_RECV windows of every rank first");
+  }
+  ctx->peer_direct = enable != 0;
   return NFH_OK;
 }
 

@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(kScanThreads)
 estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ dist, const double *__restrict__ indF,
                   const double *__restrict__ alpha, const double4 *__restrict__ chunk_prod,
                   const double2 *__restrict__ fwd_carry, const double2 *__restrict__ bwd_carry,
-                  double *__restrict__ post, int *__restrict__ status, uint64_t n_rows, uint64_t n_sites,
-                  uint64_t site_block, uint32_t n_tiles) {
+                  double *__restrict__ post, PeerWindows peers, int *__restrict__ status, uint64_t n_rows,
+                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
   const uint32_t tile = blockIdx.x, row = blockIdx.y;
@@ -343,7 +343,14 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
   fence_async_shared();
   __syncthreads();
   if (threadIdx.x == 0) {
-    tma_store_1d(post + tile_at, sm.r, kTileBytes);
+    tma_store_1d(post + tile_at, sm.r, kTileBytes);       // individual-major copy (output, nfh_get_posterior)
+    if (peers.direct) {
+      // this tile belongs to site block b: also store it into rank b's frequency-side window over
+      // NVLink, source block = me - the posterior "all-to-all" happens inside this kernel
+      const uint64_t b = tile_first / site_block;
+      double *dst = peers.base[b] + ((uint64_t) peers.rank * n_rows + row) * site_block + (tile_first - b * site_block);
+      tma_store_1d(dst, sm.r, kTileBytes);
+    }
     tma_store_wait_read();
   }
 }
@@ -509,8 +516,8 @@ void launch_estep(const EstepArgs &a, cudaStream_t st) {
       a.tile_prod, a.indF, a.loge0_sum, a.fwd_carry, a.bwd_carry, a.ind_lkl, a.status, (uint32_t) a.n_rows_valid,
       a.n_tiles);
   estep_chunk_apply<<<grid, kScanThreads, sizeof(TileSmem), st>>>(a.emis, a.dist, a.indF, a.alpha, a.chunk_prod,
-                                                                  a.fwd_carry, a.bwd_carry, a.post, a.status, a.n_rows,
-                                                                  a.n_sites, a.site_block, a.n_tiles);
+                                                                  a.fwd_carry, a.bwd_carry, a.post, a.post_peers, a.status,
+                                                                  a.n_rows, a.n_sites, a.site_block, a.n_tiles);
 }
 
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st) {

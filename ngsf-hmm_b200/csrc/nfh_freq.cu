@@ -127,6 +127,14 @@ __device__ __forceinline__ void pass_sums(const double (&a0)[K], const double (&
   pd = a * (A3 + B3);
 }
 
+// Where the refreshed emission of (individual i, local site) goes: the local window, or - in direct
+// mode - the recursion-side window of the rank that owns individual i, source block = this rank.
+__device__ __forceinline__ double *emis_slot(const FreqArgs &A, uint64_t i, uint64_t site) {
+  if (!A.emis_peers.direct) return A.emis + (size_t) i * A.site_block + site;
+  const uint64_t owner = i / A.emis_peers.n_loc, il = i - owner * A.emis_peers.n_loc;
+  return A.emis_peers.base[owner] + ((uint64_t) A.emis_peers.rank * A.emis_peers.n_loc + il) * A.site_block + site;
+}
+
 // state emissions from linear GL at frequency f (calc_emission with F = 0 / 1)
 __device__ __forceinline__ void emissions(double L0, double L1, double L2, double f, double &e0, double &e1) {
   double omf = 1.0 - f;
@@ -210,7 +218,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
         const size_t at = (size_t) i * A.site_block + site;
         double e0, e1;
         emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
-        A.emis[at] = e1 / e0;
+        *emis_slot(A, i, site) = e1 / e0;
         if (A.e0) A.e0[at] = e0;
         le0 = log(e0);
       }
@@ -321,7 +329,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         const size_t at = (size_t) i * A.site_block + site;
         double e0, e1;
         emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
-        A.emis[at] = e1 / e0;
+        *emis_slot(A, i, site) = e1 / e0;
         if (A.e0) A.e0[at] = e0;
         my_acc[i] += log(e0);                           // each (team, individual) slot has one writer
       }
@@ -368,7 +376,7 @@ freq_emission_stream(FreqArgs A) {
       const size_t at = (size_t) i * A.site_block + site;
       double e0, e1;
       emissions(A.gl0[at], A.gl1[at], A.gl2[at], freq, e0, e1);
-      A.emis[at] = e1 / e0;
+      *emis_slot(A, i, site) = e1 / e0;
       if (A.e0) A.e0[at] = e0;
     }
   }

@@ -8,6 +8,18 @@ namespace nfh {
 
 constexpr int kMaxPoints = 5;   // objective points per individual per round: x, x -/+ eh_F, x -/+ eh_alpha (bfgs.cpp:22-43)
 
+constexpr int kMaxRanks = 8;
+
+// Destination windows of the other ranks (CUDA IPC mappings over NVLink).  When `direct` is set the
+// producing kernel stores straight into the window of the rank that owns the data next, instead of a
+// local send window that an all-to-all would move afterwards.
+struct PeerWindows {
+  double *base[kMaxRanks];
+  uint64_t n_loc;      // individuals per rank (rows per source block)
+  int rank;            // this rank = source block index in the destination window
+  int direct;
+};
+
 struct TileProd {   // product of one tile's site matrices: [[a b][c d]] * 2^e * exp(l)
   double a, b, c, d, e, l;
 };
@@ -31,6 +43,7 @@ struct EstepArgs {
   TileProd *tile_prod;       // [n_rows][n_tiles]
   double2 *fwd_carry, *bwd_carry;   // per tile
   double *post;              // blocked like emis
+  PeerWindows post_peers;    // destination of posterior tile b = rank b's window
   double *ind_lkl;
   int *status;
   uint64_t n_rows, n_rows_valid, n_sites, site_block;
@@ -52,6 +65,7 @@ struct FreqArgs {
   double *freq;                   // [site_block]
   double *emis;                   // out: e1/e0  [n_ind_pad][site_block]
   double *e0;                     // out: e0 or NULL
+  PeerWindows emis_peers;         // destination of row i = owner of individual i
   double *loge0_part;             // out: [gridDim.x][n_ind_pad] partial sums of log e0
   uint64_t n_ind, n_ind_pad, site_block, sites_owned;
   int update_freq;                // 1: run est_maf; 0: keep freq

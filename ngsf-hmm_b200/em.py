@@ -72,6 +72,10 @@ class EmRank:
         self.total_rounds = 0
         self._win = {}
         self._ext_stream = None
+        self._side = None
+        self._post_done = None
+        self.direct = False
+        self._token = None
 
     # -- multi-rank plumbing ------------------------------------------------
     def _tensor(self, which):
@@ -96,6 +100,29 @@ class EmRank:
         with self._stream_ctx():
             exchange_all_to_all(self._tensor(api.WIN_POST_SEND), self._tensor(api.WIN_POST_RECV), self.group)
 
+    def exchange_posteriors_begin(self):
+        """Start the posterior all-to-all on a side stream (ordered after everything queued on the context
+        stream so far) so that it overlaps the F/alpha update, which only reads the emission window."""
+        if self.ctx.n_ranks == 1:
+            return
+        import torch
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+            self._ext_stream = self._ext_stream or torch.cuda.ExternalStream(self.ctx.stream)
+        ready = torch.cuda.Event()
+        ready.record(self._ext_stream)
+        self._side.wait_event(ready)
+        with torch.cuda.stream(self._side):
+            exchange_all_to_all(self._tensor(api.WIN_POST_SEND), self._tensor(api.WIN_POST_RECV), self.group)
+            self._post_done = torch.cuda.Event()
+            self._post_done.record(self._side)
+
+    def exchange_posteriors_end(self):
+        if self.ctx.n_ranks == 1 or self._post_done is None:
+            return
+        self._ext_stream.wait_event(self._post_done)      # the frequency kernel is queued behind the exchange
+        self._post_done = None
+
     def exchange_emissions(self, with_e0=False):
         if self.ctx.n_ranks == 1:
             return
@@ -106,10 +133,47 @@ class EmRank:
                 exchange_all_to_all(self._tensor(api.WIN_E0_SEND), self._tensor(api.WIN_E0_RECV), self.group)
             dist.all_reduce(self._tensor(api.WIN_LOGE0_SUM), group=self.group)
 
+    def enable_peer_direct(self):
+        """Fused exchange: all-gather the CUDA IPC handles of every rank's receive windows and let the
+        E-step / frequency kernels store straight into the owner's window over NVLink."""
+        if self.ctx.n_ranks == 1:
+            return False
+        import torch
+        import torch.distributed as dist
+        for which in (api.WIN_POST_RECV, api.WIN_EMIS_RECV):
+            mine = self.ctx.peer_export(which)
+            handles = [None] * self.ctx.n_ranks
+            dist.all_gather_object(handles, mine, group=self.group)
+            for r, h in enumerate(handles):
+                self.ctx.peer_import(which, r, h)
+        self.ctx.peer_direct(True)
+        self.direct = True
+        self._token = torch.zeros(1, device=f"cuda:{torch.cuda.current_device()}")
+        return True
+
+    def _rank_fence(self):
+        """Order the stages across ranks on the context stream: completes only after every rank has
+        reached it in its own stream, i.e. after the kernels it queued before (1-element all-reduce)."""
+        import torch.distributed as dist
+        with self._stream_ctx():
+            dist.all_reduce(self._token, group=self.group)
+
+    def _allreduce_loge0(self):
+        import torch.distributed as dist
+        with self._stream_ctx():
+            dist.all_reduce(self._tensor(api.WIN_LOGE0_SUM), group=self.group)
+
     # -- iteration ----------------------------------------------------------
     def refresh_emissions(self, with_e0=False):
         self.ctx.emission_refresh(with_e0)
-        self.exchange_emissions(with_e0)
+        if self.direct:
+            # ratios were stored into the owners' windows by the kernel; e0 (Viterbi only) still travels by NCCL
+            if with_e0:
+                with self._stream_ctx():
+                    exchange_all_to_all(self._tensor(api.WIN_E0_SEND), self._tensor(api.WIN_E0_RECV), self.group)
+            self._allreduce_loge0()                      # doubles as the cross-rank fence for the stores
+        else:
+            self.exchange_emissions(with_e0)
 
     def bfgs_update(self, indF, alpha):
         n = self.ctx.n_ind_owned
@@ -135,12 +199,19 @@ class EmRank:
             return lk, fr
         ctx.set_ind_params(indF, alpha)
         lk = ctx.estep()
-        self.exchange_posteriors()                       # overlaps with the host/device BFGS rounds below
+        if self.freq_est and not self.direct:
+            self.exchange_posteriors_begin()             # overlaps the host/device BFGS rounds below
         self.bfgs_update(indF, alpha)
         fr = None
         if self.freq_est:
-            fr = ctx.freq_update(1, want_freq=want_freq)
-            self.exchange_emissions()
+            if self.direct:
+                self._rank_fence()                       # every rank's E-step stores have landed
+                fr = ctx.freq_update(1, want_freq=want_freq)
+                self._allreduce_loge0()                  # + fence: every rank's emission stores have landed
+            else:
+                self.exchange_posteriors_end()
+                fr = ctx.freq_update(1, want_freq=want_freq)
+                self.exchange_emissions()
         return lk, fr
 
 
