@@ -238,16 +238,20 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
 }
 
 // Teams of W warps share one site (32 W lanes, K individuals per lane): the
-// register-resident scheme for 128 < n_ind <= 4096, e.g. the frequency side of
+// register-resident scheme for 512 < n_ind <= 4096, e.g. the frequency side of
 // a multi-rank run, which always sees ALL individuals.  Per pass the lanes of a
-// warp reduce by shuffles, the W warps of a team through shared memory (one
-// barrier per pass, partials double-buffered by pass parity).
-constexpr int kTeamThreads = 256;
+// warp reduce by shuffles and the W warps of a team through shared memory with
+// a NAMED barrier of the team only (partials double-buffered by pass parity):
+// teams work on different sites and never wait for each other, and the CTA is
+// kept small (128 threads for W <= 4) so that two CTAs share an SM.
+__device__ __forceinline__ void team_barrier(int team, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(n_threads) : "memory");
+}
 
-template <int W, int K>
-__global__ void __launch_bounds__(kTeamThreads)
+template <int W, int K, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
-  constexpr int kWarps = kTeamThreads / 32;
+  constexpr int kWarps = THREADS / 32;
   constexpr int kTeams = kWarps / W;
   constexpr int G = 32 * W;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -256,7 +260,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
   extern __shared__ double team_smem[];                 // [kTeams][n_ind_pad] log e0 accumulators
   __shared__ double2 part[2][kTeams][W];
   __shared__ double gpart[kTeams][W];
-  for (unsigned i = threadIdx.x; i < kTeams * A.n_ind_pad; i += kTeamThreads) team_smem[i] = 0.0;
+  for (unsigned i = threadIdx.x; i < kTeams * A.n_ind_pad; i += THREADS) team_smem[i] = 0.0;
   __syncthreads();
   double *my_acc = team_smem + (size_t) team * A.n_ind_pad;
 
@@ -287,15 +291,15 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
 #pragma unroll
       for (int m = 1; m < 32; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
       if (lane == 0) gpart[team][wt] = g_sum;
-      __syncthreads();
+      team_barrier(team, G);
       g_sum = 0.0;
 #pragma unroll
       for (int w = 0; w < W; w++) g_sum += gpart[team][w];
 
       double num = 0.0, den = 0.0;
-      bool active = site_ok;
+      bool active = site_ok;                            // identical in every thread of the team
       int passes = 0;
-      while (__syncthreads_or(active)) {                // also orders the previous pass's reads before new writes
+      while (active) {
         const double omf = 1.0 - freq;
         const double u = omf * omf, v = freq * freq, a = omf * freq;
         double pn, pd;
@@ -307,19 +311,18 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         }
         const int buf = passes & 1;
         if (lane == 0) part[buf][team][wt] = make_double2(pn, pd);
-        __syncthreads();
+        team_barrier(team, G);
         pn = 0.0; pd = g_sum;
 #pragma unroll
         for (int w = 0; w < W; w++) { const double2 q = part[buf][team][w]; pn += q.x; pd += q.y; }
         passes++;
-        if (active) {
-          num += pn; den += pd;
-          const double before = freq;
-          freq = num * rcp_pos<true>(den);
-          active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
-        }
+        num += pn; den += pd;
+        const double before = freq;
+        freq = num * rcp_pos<true>(den);
+        active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
       }
       if (site_ok && grp == 0) A.freq[site] = freq;
+      team_barrier(team, G);                            // gpart / part are reused by the next tile
     }
 
 #pragma unroll
@@ -336,7 +339,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
     }
   }
   __syncthreads();
-  for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kTeamThreads) {
+  for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += THREADS) {
     double s = 0.0;
 #pragma unroll
     for (int t = 0; t < kTeams; t++) s += team_smem[(size_t) t * A.n_ind_pad + i];
@@ -510,7 +513,7 @@ unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   int G, K, W;
   unsigned per_cta = 0;
   if (pick_shape(a.n_ind, G, K)) per_cta = (32 / G) * (kFreqThreads / 32);
-  else if (pick_team_shape(a.n_ind, W, K)) per_cta = (kTeamThreads / 32) / W;
+  else if (pick_team_shape(a.n_ind, W, K)) per_cta = ((W <= 4 ? 128 : 256) / 32) / W;
   if (per_cta) {
     unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
     unsigned cap = (unsigned) sm_count * 4u;
@@ -529,15 +532,16 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
 
 template <int W, int K>
 static void launch_team_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  constexpr int kTeams = (kTeamThreads / 32) / W;
+  constexpr int kThreads = W <= 4 ? 128 : 256;
+  constexpr int kTeams = (kThreads / 32) / W;
   const unsigned tiles = (unsigned) ((a.sites_owned + kTeams - 1) / kTeams);
   size_t smem = (size_t) kTeams * a.n_ind_pad * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_team<W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(freq_emission_team<W, K, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     attr_done = true;
   }
-  freq_emission_team<W, K><<<grid, kTeamThreads, smem, st>>>(a, tiles);
+  freq_emission_team<W, K, kThreads><<<grid, kThreads, smem, st>>>(a, tiles);
 }
 
 #define NFH_K_CASES(MACRO)                                                                          \
