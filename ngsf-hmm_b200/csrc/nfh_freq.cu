@@ -145,22 +145,61 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
 }
 
 // G lanes share one site (G divides 32); each lane keeps K individuals.
-template <int G, int K>
+//
+// PREFETCH: the CTA's next site tile (GL x3 + posterior rows of all individuals, 16-32 sites wide)
+// is fetched into shared memory by TMA bulk copies while the current tile runs its ~101 passes, so
+// the set-up of a tile reads shared memory instead of waiting on HBM (ncu r01c: long-scoreboard
+// stalls were 18 % of the kernel).  Two buffers, one mbarrier each.
+template <int G, int K, bool PREFETCH>
 __global__ void __launch_bounds__(kFreqThreads)
 freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
   constexpr int kSitesPerWarp = 32 / G;
   constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
+  constexpr uint32_t kRowBytes = kSitesPerCta * sizeof(double);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane & (G - 1), sub = lane / G;
-  extern __shared__ double loge0_acc[];     // [warps][n_ind_pad]
+  extern __shared__ __align__(128) double freq_smem[];     // [warps][n_ind_pad] log e0, then the tile buffers
+  double *loge0_acc = freq_smem;
   for (unsigned i = threadIdx.x; i < (kFreqThreads / 32) * A.n_ind_pad; i += kFreqThreads) loge0_acc[i] = 0.0;
-  __syncthreads();
   double *my_acc = loge0_acc + (size_t) warp * A.n_ind_pad;
 
-  for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x) {
-    const uint64_t site = (uint64_t) tile * kSitesPerCta + warp * kSitesPerWarp + sub;
+  // ---- prefetch machinery
+  const unsigned n_planes = A.post ? 4u : 3u;
+  const unsigned n_rows = n_planes * (unsigned) A.n_ind;
+  const size_t buf_doubles = (size_t) 4 * A.n_ind * kSitesPerCta;
+  const size_t acc_doubles = (((size_t) (kFreqThreads / 32) * A.n_ind_pad + 15) / 16) * 16;
+  double *bufs = freq_smem + acc_doubles;
+  __shared__ alignas(8) uint64_t bars[2];
+  auto issue_tile = [&](unsigned t, int b) {
+    // rows r = plane * n_ind + i: kSitesPerCta consecutive sites of individual i in that plane
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bars[b], n_rows * kRowBytes);
+    __syncthreads();
+    const uint64_t first_site = (uint64_t) t * kSitesPerCta;
+    for (unsigned r = threadIdx.x; r < n_rows; r += kFreqThreads) {
+      const unsigned plane = r / (unsigned) A.n_ind, i = r - plane * (unsigned) A.n_ind;
+      const double *src = (plane == 0 ? A.gl0 : plane == 1 ? A.gl1 : plane == 2 ? A.gl2 : A.post) +
+                          (size_t) i * A.site_block + first_site;
+      tma_load_1d(bufs + (size_t) b * buf_doubles + ((size_t) plane * A.n_ind + i) * kSitesPerCta, src, kRowBytes,
+                  &bars[b]);
+    }
+  };
+  if (PREFETCH) {
+    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+  }
+  __syncthreads();
+  if (PREFETCH && blockIdx.x < n_site_tiles) issue_tile(blockIdx.x, 0);
+
+  unsigned round = 0;
+  for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x, round++) {
+    const int site_in_cta = warp * kSitesPerWarp + sub;
+    const uint64_t site = (uint64_t) tile * kSitesPerCta + site_in_cta;
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
+    const double *tile_buf = bufs + (size_t) (round & 1) * buf_doubles;
+    if (PREFETCH) {
+      if (tile + gridDim.x < n_site_tiles) issue_tile(tile + gridDim.x, (round & 1) ^ 1);
+      mbar_wait(&bars[round & 1], (round >> 1) & 1);
+    }
 
     double a0[K], a2[K], hh[K], na[K], nv[K], da[K];
     double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
@@ -169,9 +208,19 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
       IndCoef c;
       if (i < A.n_ind) {
-        const size_t at = (size_t) i * A.site_block + sl;
-        const double F = A.post ? A.post[at] : 0.0;
-        c = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
+        double L0, L1, L2, F;
+        if (PREFETCH) {
+          const double *row = tile_buf + i * kSitesPerCta + site_in_cta;
+          const size_t plane = (size_t) A.n_ind * kSitesPerCta;
+          L0 = row[0]; L1 = row[plane]; L2 = row[2 * plane];
+          F = A.post ? row[3 * plane] : 0.0;
+          if (!site_ok) { L0 = 1.0 / 3; L1 = 1.0 / 3; L2 = 1.0 / 3; F = 0.0; }   // padding sites: harmless values
+        } else {
+          const size_t at = (size_t) i * A.site_block + sl;
+          L0 = A.gl0[at]; L1 = A.gl1[at]; L2 = A.gl2[at];
+          F = A.post ? A.post[at] : 0.0;
+        }
+        c = make_coef(L0, L1, L2, F);
       } else {
         c = null_coef();
       }
@@ -216,9 +265,10 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       double le0 = 0.0;
       if (i < A.n_ind && site_ok) {
         const size_t at = (size_t) i * A.site_block + site;
+        const double L1 = PREFETCH ? tile_buf[((size_t) A.n_ind + i) * kSitesPerCta + site_in_cta] : A.gl1[at];
         double e0, e1;
-        emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
-        *emis_slot(A, i, site) = e1 / e0;
+        emissions(a0[k], L1, a2[k], freq, e0, e1);
+        *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
         if (A.e0) A.e0[at] = e0;
         le0 = log(e0);
       }
@@ -227,6 +277,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       for (int m = G; m < 32; m <<= 1) le0 += __shfl_xor_sync(kFull, le0, m);
       if (sub == 0 && i < A.n_ind_pad) my_acc[i] += le0;
     }
+    if (PREFETCH) __syncthreads();            // the buffer is refilled two tiles from now
   }
   __syncthreads();
   for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kFreqThreads) {
@@ -526,8 +577,17 @@ template <int G, int K>
 static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
   const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
-  size_t smem = (size_t) (kFreqThreads / 32) * a.n_ind_pad * sizeof(double);
-  freq_emission_warp<G, K><<<grid, kFreqThreads, smem, st>>>(a, tiles);
+  const size_t acc = ((((size_t) (kFreqThreads / 32) * a.n_ind_pad + 15) / 16) * 16) * sizeof(double);
+  const size_t bufs = (size_t) 2 * 4 * a.n_ind * per_cta * sizeof(double);
+  // two CTAs per SM must fit their double buffers in the 227 KB of shared memory
+  const bool prefetch = acc + bufs <= 108 * 1024 && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    attr_done = true;
+  }
+  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
+  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles);
 }
 
 template <int W, int K>
