@@ -40,8 +40,8 @@ START_FREQ, START_F, START_ALPHA = 0.1, 0.1, 0.2
 ESTEP_BYTES_PER_IND_SITE = 24.0          # read 2 emissions, write 1 posterior
 FREQ_FLOPS_PER_IND_PASS = 15.0           # linear-space est_maf contribution: 9 FP64 instructions (6 of them FMA)
 FREQ_PASSES = 101.0                      # upper bound per site (gen_func.cpp:1006); ~90% of sites hit it
-LKL_FLOPS_PER_IND_SITE_POINT = 24.0      # 2x2 product update (12 flop-slots, 6 of them FMA) per objective point
-EXP_FLOPS = 32.0                         # one FP64 exp() = 14 DFMA + 2 DADD + range handling
+LKL_FLOPS_PER_IND_SITE_POINT = 14.0      # factored 2x2 update: 2 ADD + 4 FMA + 4 MUL per objective point and site
+EXP_FLOPS = 21.0                         # kappa = expm1(alpha d): 13 FP64 instructions, 8 of them FMA; 3 per 5 points
 
 
 def parse_args():
@@ -104,6 +104,16 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_traffic():
+    """DRAM bytes per individual-site measured by ncu (committed under profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01c.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["bytes_per_ind_site"]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peaks():
@@ -281,15 +291,19 @@ def main():
         lkl_flops = (LKL_FLOPS_PER_IND_SITE_POINT + 0.6 * EXP_FLOPS) * evals_step * S
         lkl_tf = lkl_flops / (per_step["lkl_batch"] * 1e-3) / 1e12 if per_step["lkl_batch"] > 0 else 0.0
         dominant = max(("estep", "lkl_batch", "freq"), key=lambda k: per_step[k])
+        traffic = ncu_traffic() or {}
+        t_estep = traffic.get("estep") and traffic["estep"] * rank_units
+        t_freq = traffic.get("freq") and traffic["freq"] * freq_units
+        t_lkl = traffic.get("lkl_batch_per_group_site") and traffic["lkl_batch_per_group_site"] * rank_units  # a round with every individual active
         roof_estep = {"kernel": "estep (tile_products + carries + apply)", "bound": "hbm", "achieved": estep_gbs,
-                      "peak": hbm_peak, "unit": "GB/s", "frac": estep_gbs / hbm_peak, "traffic": None,
+                      "peak": hbm_peak, "unit": "GB/s", "frac": estep_gbs / hbm_peak, "traffic": t_estep,
                       "peak_source": peak_src, "ms_per_step": per_step["estep"]}
         roof_freq = {"kernel": "freq_emission_warp", "bound": "fp64", "achieved": freq_tf,
                      "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": freq_tf / (fp64_peak / 1e12),
-                     "traffic": None, "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
+                     "traffic": t_freq, "instruction_mix_ceiling": 15.0 / 18.0, "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
                      "ms_per_step": per_step["freq"]}
         roof_lkl = {"kernel": "lkl_tile_products", "bound": "fp64", "achieved": lkl_tf, "peak": fp64_peak / 1e12,
-                    "unit": "TFLOP/s", "frac": lkl_tf / (fp64_peak / 1e12), "traffic": None,
+                    "unit": "TFLOP/s", "frac": lkl_tf / (fp64_peak / 1e12), "traffic": t_lkl,
                     "peak_source": "measured live: DFMA probe kernel", "ms_per_step": per_step["lkl_batch"]}
         roofs = {"estep": roof_estep, "freq": roof_freq, "lkl_batch": roof_lkl}
         out = {
