@@ -42,8 +42,11 @@ struct IndCoef {   // pass-invariant coefficients of one individual at one site
 //   den += (2 w1 + (w0+w2) g)/S = g + F w1 / S  = g + [ 2 L1 (1-F) F a ] / S
 // so per pass and individual only S, 1/S and three FMAs into
 //   A1 = sum na/S,  A2 = sum nv/S,  A3 = sum da/S
-// are needed (9 FP64 instructions); num = a A1 + v A2 and den = sum g + a A3
-// are formed once per pass.
+// are needed; num = a A1 + v A2 and den = sum g + a A3 are formed once per pass.
+// The register kernels divide everything by u and work with the allele odds
+// t = f/(1-f) = num/(den-num):  S/u = a0 + h t + a2 t^2 is two Horner FMAs, so an
+// individual costs 8 FP64 instructions per pass (2 + 3 for its share of a
+// four-way reciprocal + 3), and num = t (A1 + t A2), den = sum g + t A3.
 __device__ __forceinline__ IndCoef make_coef(double L0, double L1, double L2, double F) {
   IndCoef k;
   double c1 = 2.0 * L1 * (1.0 - F);
@@ -108,14 +111,15 @@ __device__ __forceinline__ void reciprocals(const double (&S)[K], double (&inv)[
   }
 }
 
-// One pass over a lane's K individuals: pn = sum (w1 + g w2)/S, pd = sum F w1/S.
+// One pass over a lane's K individuals at allele odds t = f/(1-f):
+// pn = sum (w1 + g w2)/S, pd = sum F w1/S.
 template <int K>
 __device__ __forceinline__ void pass_sums(const double (&a0)[K], const double (&a2)[K], const double (&hh)[K],
                                           const double (&na)[K], const double (&nv)[K], const double (&da)[K],
-                                          double u, double v, double a, double &pn, double &pd) {
+                                          double t, double &pn, double &pd) {
   double S[K], inv[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) S[k] = fma(a0[k], u, fma(a2[k], v, hh[k] * a));
+  for (int k = 0; k < K; k++) S[k] = fma(fma(a2[k], t, hh[k]), t, a0[k]);
   reciprocals<K>(S, inv);
   double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;   // two interleaved accumulator sets
 #pragma unroll
@@ -123,9 +127,17 @@ __device__ __forceinline__ void pass_sums(const double (&a0)[K], const double (&
     if (k & 1) { B1 = fma(na[k], inv[k], B1); B2 = fma(nv[k], inv[k], B2); B3 = fma(da[k], inv[k], B3); }
     else       { A1 = fma(na[k], inv[k], A1); A2 = fma(nv[k], inv[k], A2); A3 = fma(da[k], inv[k], A3); }
   }
-  pn = fma(a, A1 + B1, v * (A2 + B2));
-  pd = a * (A3 + B3);
+  pn = t * fma(t, A2 + B2, A1 + B1);
+  pd = t * (A3 + B3);
 }
+
+// est_maf starts every site at f = 0.01 (gen_func.cpp:980)
+constexpr double kStartFreq = 0.01;
+constexpr double kStartOdds = 0.01 / 0.99;
+
+// Resident CTAs per SM the register budget of K individuals per lane allows
+// (12 K registers of coefficients + 4 K of per-pass temporaries + ~40).
+__host__ __device__ constexpr int freq_occupancy(int K) { return K <= 4 ? 4 : K <= 8 ? 3 : 2; }
 
 // Where the refreshed emission of (individual i, local site) goes: the local window, or - in direct
 // mode - the recursion-side window of the rank that owns individual i, source block = this rank.
@@ -150,8 +162,8 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
 // is fetched into shared memory by TMA bulk copies while the current tile runs its ~101 passes, so
 // the set-up of a tile reads shared memory instead of waiting on HBM (ncu r01c: long-scoreboard
 // stalls were 18 % of the kernel).  Two buffers, one mbarrier each.
-template <int G, int K, bool PREFETCH>
-__global__ void __launch_bounds__(kFreqThreads)
+template <int G, int K, bool PREFETCH, int OCC = freq_occupancy(K)>
+__global__ void __launch_bounds__(kFreqThreads, OCC)
 freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
   constexpr int kSitesPerWarp = 32 / G;
   constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
@@ -228,18 +240,16 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       g_sum += c.g;
     }
 
-    double freq = A.update_freq ? 0.01 : A.freq[sl];
+    double freq = A.update_freq ? kStartFreq : A.freq[sl];
     if (A.update_freq) {
 #pragma unroll
       for (int m = 1; m < G; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
-      double num = 0.0, den = 0.0;
+      double num = 0.0, den = 0.0, odds = kStartOdds;
       bool active = site_ok;
       int passes = 0;
       while (__any_sync(kFull, active)) {
-        const double omf = 1.0 - freq;
-        const double u = omf * omf, v = freq * freq, a = omf * freq;
         double pn, pd;
-        pass_sums<K>(a0, a2, hh, na, nv, da, u, v, a, pn, pd);
+        pass_sums<K>(a0, a2, hh, na, nv, da, odds, pn, pd);
 #pragma unroll
         for (int m = 1; m < G; m <<= 1) {
           pn += __shfl_xor_sync(kFull, pn, m);
@@ -250,7 +260,8 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
         if (active) {
           num += pn; den += pd;
           const double before = freq;
-          freq = num * rcp_pos<true>(den);
+          odds = num * rcp_pos<true>(den - num);        // feeds the next pass
+          freq = num * rcp_pos<true>(den);              // independent of it: only the stop test waits
           // do { ... } while (|before - freq| > EPSILON && iters++ < 100)   gen_func.cpp:1006
           active = (fabs(before - freq) > kEps) && (passes <= 100);
         }
@@ -337,7 +348,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
       g_sum += c.g;
     }
 
-    double freq = A.update_freq ? 0.01 : A.freq[sl];
+    double freq = A.update_freq ? kStartFreq : A.freq[sl];
     if (A.update_freq) {
 #pragma unroll
       for (int m = 1; m < 32; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
@@ -347,14 +358,12 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
 #pragma unroll
       for (int w = 0; w < W; w++) g_sum += gpart[team][w];
 
-      double num = 0.0, den = 0.0;
+      double num = 0.0, den = 0.0, odds = kStartOdds;
       bool active = site_ok;                            // identical in every thread of the team
       int passes = 0;
       while (active) {
-        const double omf = 1.0 - freq;
-        const double u = omf * omf, v = freq * freq, a = omf * freq;
         double pn, pd;
-        pass_sums<K>(a0, a2, hh, na, nv, da, u, v, a, pn, pd);
+        pass_sums<K>(a0, a2, hh, na, nv, da, odds, pn, pd);
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) {
           pn += __shfl_xor_sync(kFull, pn, m);
@@ -369,6 +378,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         passes++;
         num += pn; den += pd;
         const double before = freq;
+        odds = num * rcp_pos<true>(den - num);
         freq = num * rcp_pos<true>(den);
         active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
       }
@@ -563,11 +573,12 @@ static bool pick_team_shape(uint64_t n_ind, int &W, int &K) {
 unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   int G, K, W;
   unsigned per_cta = 0;
-  if (pick_shape(a.n_ind, G, K)) per_cta = (32 / G) * (kFreqThreads / 32);
+  unsigned ctas_per_sm = 4;
+  if (pick_shape(a.n_ind, G, K)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = freq_occupancy(K); }
   else if (pick_team_shape(a.n_ind, W, K)) per_cta = ((W <= 4 ? 128 : 256) / 32) / W;
   if (per_cta) {
     unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
-    unsigned cap = (unsigned) sm_count * 4u;
+    unsigned cap = (unsigned) sm_count * ctas_per_sm;   // persistent CTAs: one resident wave
     return tiles < cap ? (tiles ? tiles : 1u) : cap;
   }
   return 64;   // chunks of loge0_rowsum
@@ -579,12 +590,18 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t acc = ((((size_t) (kFreqThreads / 32) * a.n_ind_pad + 15) / 16) * 16) * sizeof(double);
   const size_t bufs = (size_t) 2 * 4 * a.n_ind * per_cta * sizeof(double);
-  // two CTAs per SM must fit their double buffers in the 227 KB of shared memory
-  const bool prefetch = acc + bufs <= 108 * 1024 && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
+  // all resident CTAs of an SM must fit their double buffers in its 227 KB of shared memory (1 KB reserved each)
+  const size_t smem_cap = (size_t) 227 * 1024 / freq_occupancy(K) - 2048;
+  const bool prefetch = acc + bufs <= smem_cap && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
     attr_done = true;
+  }
+  if (G == 16 && K == 7 && getenv("NFH_FREQ_OCC4")) {   // experiment: 128-register build, four CTAs per SM
+    cudaFuncSetAttribute(freq_emission_warp<16, 7, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+    freq_emission_warp<16, 7, true, 4><<<grid * 4 / 3, kFreqThreads, acc + bufs, st>>>(a, tiles);
+    return;
   }
   if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
   else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles);
