@@ -360,40 +360,65 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
 // individual share one staged read of its emissions.
 // ---------------------------------------------------------------------------
 
+constexpr int kLklThreads = 2 * kScanThreads;   // two halves share one staged tile, each takes part of the points
+
 struct LklSmem {
-  TileSmem t;
+  alignas(128) double r[kTile];     // emission ratio
+  alignas(128) double d[kTile];     // distance (Mb)
+  alignas(8) uint64_t bar;
+  double tab[64];
   M2 m[kMaxPoints][kScanThreads / 32];
   int e[kMaxPoints][kScanThreads / 32];
   double l[kMaxPoints][kScanThreads / 32];
 };
 
-// NS leading points share alpha (one kappa per site for all of them); the next NA points each have
-// their own.  The layout is fixed per group, so the whole body is straight-line code.
+// FP64 instructions per site of a set of points: 13 per distinct alpha (kappa) + 10 per point (2x2 update)
+__host__ __device__ constexpr int lkl_cost(int n_same, int n_other) {
+  return 13 * ((n_same > 0 ? 1 : 0) + n_other) + 10 * (n_same + n_other);
+}
+// The points of a group are ordered [NS sharing alpha[0]] [NA with their own alpha].  The first k go to
+// half 0 of the CTA, the rest to half 1; k balances the two instruction counts.
+__host__ __device__ constexpr int lkl_split(int NS, int NA) {
+  int best = 1, best_cost = 1 << 30;
+  for (int k = 1; k <= NS + NA; k++) {
+    const int sa = k < NS ? k : NS, oa = k - sa;
+    const int ca = lkl_cost(sa, oa), cb = lkl_cost(NS - sa, NA - oa);
+    const int c = ca > cb ? ca : cb;
+    if (c < best_cost) { best_cost = c; best = k; }
+  }
+  return best;
+}
+
+// One thread's chunk of kChunk sites for points [first, first + NS + NA) of the group: the first NS
+// share alpha[first] (one kappa per site for all of them), the next NA each have their own.  The
+// layout is fixed per group, so the whole body is straight-line code.  Lane 0 of every warp leaves
+// the warp's ordered product in shared memory.
 template <int NS, int NA>
-__device__ __forceinline__ void lkl_tile_body(const LklGroup &g, LklSmem &sm, int n_valid,
-                                              TileProd *__restrict__ out_row, uint32_t n_tiles, uint32_t tile) {
+__device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklSmem &sm, int t, int n_valid) {
   constexpr int NP = NS + NA;
   constexpr int kBody = 6;
-  const double *r = sm.t.r + threadIdx.x * kChunk;
-  const double *d = sm.t.d + threadIdx.x * kChunk;
+  const double *r = sm.r + t * kChunk;
+  const double *d = sm.d + t * kChunk;
   M2 m[NP];
   int e[NP];
   double ls[1 + NA];          // scale sums: one for the shared alpha, one per extra alpha
   double q1[NP], q0[NP];
 #pragma unroll
-  for (int p = 0; p < NP; p++) { m[p] = identity2(); e[p] = 0; q1[p] = g.F[p]; q0[p] = 1.0 - g.F[p]; }
+  for (int p = 0; p < NP; p++) { m[p] = identity2(); e[p] = 0; q1[p] = g.F[first + p]; q0[p] = 1.0 - g.F[first + p]; }
 #pragma unroll
   for (int a = 0; a <= NA; a++) ls[a] = 0.0;
 
   auto site = [&](int j) {
     const double dj = d[j];
     const double rj = j < n_valid ? r[j] : 1.0;      // padding: identity (d = 0 -> kappa = 0)
-    const double ks = site_kappa(g.alpha[0] * dj, sm.t.tab, ls[0]);
+    if (NS > 0) {
+      const double ks = site_kappa(g.alpha[first] * dj, sm.tab, ls[0]);
 #pragma unroll
-    for (int p = 0; p < NS; p++) apply_site(m[p], ks * q0[p], ks * q1[p], rj);
+      for (int p = 0; p < NS; p++) apply_site(m[p], ks * q0[p], ks * q1[p], rj);
+    }
 #pragma unroll
     for (int a = 0; a < NA; a++) {
-      const double ka = site_kappa(g.alpha[NS + a] * dj, sm.t.tab, ls[1 + a]);
+      const double ka = site_kappa(g.alpha[first + NS + a] * dj, sm.tab, ls[1 + a]);
       apply_site(m[NS + a], ka * q0[NS + a], ka * q1[NS + a], rj);
     }
   };
@@ -407,7 +432,7 @@ __device__ __forceinline__ void lkl_tile_body(const LklGroup &g, LklSmem &sm, in
 #pragma unroll
   for (int j = (kChunk / kBody) * kBody; j < kChunk; j++) site(j);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (t >> 5), lane = t & 31;
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     e[p] += renorm(m[p]);
@@ -415,10 +440,60 @@ __device__ __forceinline__ void lkl_tile_body(const LklGroup &g, LklSmem &sm, in
     double l = ls[p < NS ? 0 : 1 + (p - NS)];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) l += __shfl_down_sync(kFull, l, off);
-    if (lane == 0) { sm.m[p][warp] = m[p]; sm.e[p][warp] = e[p]; sm.l[p][warp] = l; }
+    if (lane == 0) { sm.m[first + p][warp] = m[p]; sm.e[first + p][warp] = e[p]; sm.l[first + p][warp] = l; }
   }
+}
+
+template <int NS, int NA>
+__device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, int half, int t, int n_valid) {
+  constexpr int k = lkl_split(NS, NA);
+  constexpr int NSa = k < NS ? k : NS, NAa = k - NSa, NSb = NS - NSa, NAb = NA - NAa;
+  if (half == 0) {
+    lkl_chunk_run<NSa, NAa>(g, 0, sm, t, n_valid);
+  } else {
+    if constexpr (NSb + NAb > 0) lkl_chunk_run<NSb, NAb>(g, k, sm, t, n_valid);
+  }
+}
+
+// One CTA per (tile, group): the tile of emission ratios and distances is staged once by TMA and read by
+// both halves of the CTA (2 x 128 threads, each thread kChunk sites), which doubles the warps an SM can
+// hold for the same shared memory (the tile, not registers, limits occupancy: 3 CTAs per SM).
+__global__ void __launch_bounds__(kLklThreads)
+lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ dist,
+                  const LklGroup *__restrict__ groups, TileProd *__restrict__ tile_prod, uint64_t n_rows,
+                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  LklSmem &sm = *reinterpret_cast<LklSmem *>(smem_raw);
+  const uint32_t tile = blockIdx.x, grp = blockIdx.y;
+  const LklGroup g = groups[grp];
+  const uint64_t tile_first = (uint64_t) tile * kTile;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_fence_init();
+  }
+  load_exp_table(sm.tab);
   __syncthreads();
-  if ((int) threadIdx.x < NP) {
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&sm.bar, 2 * kTileBytes);
+    tma_load_1d(sm.r, emis + blocked_index((uint64_t) g.ind, tile_first, n_rows, site_block), kTileBytes, &sm.bar);
+    tma_load_1d(sm.d, dist + tile_first, kTileBytes, &sm.bar);
+  }
+  mbar_wait(&sm.bar, 0);
+  const int half = threadIdx.x / kScanThreads, t = threadIdx.x % kScanThreads;
+  const int n_valid = valid_sites(tile_first + (uint64_t) t * kChunk, n_sites);
+
+#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_halves<ns, na>(g, sm, half, t, n_valid); break;
+  switch (g.n_same * 8 + (g.npts - g.n_same)) {
+    NFH_LKL(1, 0) NFH_LKL(1, 1) NFH_LKL(1, 2) NFH_LKL(1, 3) NFH_LKL(1, 4)
+    NFH_LKL(2, 0) NFH_LKL(2, 1) NFH_LKL(2, 2) NFH_LKL(2, 3)
+    NFH_LKL(3, 0) NFH_LKL(3, 1) NFH_LKL(3, 2)
+    NFH_LKL(4, 0) NFH_LKL(4, 1)
+    NFH_LKL(5, 0)
+    default: break;
+  }
+#undef NFH_LKL
+  __syncthreads();
+  if ((int) threadIdx.x < g.npts) {
     const int p = threadIdx.x;
     M2 acc = sm.m[p][0];
     int ae = sm.e[p][0];
@@ -430,33 +505,8 @@ __device__ __forceinline__ void lkl_tile_body(const LklGroup &g, LklSmem &sm, in
     }
     TileProd out;
     out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae; out.l = al_sum;
-    out_row[(size_t) p * n_tiles + tile] = out;
+    tile_prod[((size_t) grp * kMaxPoints + p) * n_tiles + tile] = out;
   }
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ dist,
-                  const LklGroup *__restrict__ groups, TileProd *__restrict__ tile_prod, uint64_t n_rows,
-                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  LklSmem &sm = *reinterpret_cast<LklSmem *>(smem_raw);
-  const uint32_t tile = blockIdx.x, grp = blockIdx.y;
-  const LklGroup g = groups[grp];
-  const uint64_t tile_first = (uint64_t) tile * kTile;
-  stage_tile(sm.t, emis + blocked_index((uint64_t) g.ind, tile_first, n_rows, site_block), dist + tile_first);
-  const int n_valid = valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, n_sites);
-  TileProd *out_row = tile_prod + (size_t) grp * kMaxPoints * n_tiles;
-  // uniform per CTA: (points sharing alpha with point 0, further points)
-#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_body<ns, na>(g, sm, n_valid, out_row, n_tiles, tile); break;
-  switch (g.n_same * 8 + (g.npts - g.n_same)) {
-    NFH_LKL(1, 0) NFH_LKL(1, 1) NFH_LKL(1, 2) NFH_LKL(1, 3) NFH_LKL(1, 4)
-    NFH_LKL(2, 0) NFH_LKL(2, 1) NFH_LKL(2, 2) NFH_LKL(2, 3)
-    NFH_LKL(3, 0) NFH_LKL(3, 1) NFH_LKL(3, 2)
-    NFH_LKL(4, 0) NFH_LKL(4, 1)
-    NFH_LKL(5, 0)
-    default: break;
-  }
-#undef NFH_LKL
 }
 
 // One warp per (group, point): lanes take contiguous runs of tile products,
@@ -523,7 +573,7 @@ void launch_estep(const EstepArgs &a, cudaStream_t st) {
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st) {
   set_smem_attrs();
   dim3 grid(a.n_tiles, a.n_groups);
-  lkl_tile_products<<<grid, kScanThreads, sizeof(LklSmem), st>>>(a.emis, a.dist, a.groups, a.tile_prod, a.n_rows,
+  lkl_tile_products<<<grid, kLklThreads, sizeof(LklSmem), st>>>(a.emis, a.dist, a.groups, a.tile_prod, a.n_rows,
                                                                  a.n_sites, a.site_block, a.n_tiles);
   const unsigned warps = a.n_groups * kMaxPoints;
   lkl_finish<<<(warps + 3) / 4, 128, 0, st>>>(a.tile_prod, a.groups, a.loge0_sum, a.neg_lkl, a.n_groups, a.n_tiles);

@@ -35,6 +35,14 @@ struct IndCoef {   // pass-invariant coefficients of one individual at one site
   double g;              // 2 - F (only summed once per site, not used per pass)
 };
 
+// IEEE-754 binary64 exponent of a positive normal x (0 for zero, subnormal, inf and NaN) and x scaled into [1, 2)
+__device__ __forceinline__ double split_exponent(double x, int &e) {
+  const int hi = __double2hiint(x);
+  const int field = (hi >> 20) & 0x7ff;
+  e = (field == 0 || field == 0x7ff) ? 0 : field - 1023;
+  return __hiloint2double(hi - (e << 20), __double2loint(x));
+}
+
 // With u = (1-f)^2, v = f^2, a = f(1-f), GL (L0,L1,L2), IBD posterior F, g = 2 - F:
 //   w0 = L0 (u + a F)   w1 = 2 L1 (1-F) a   w2 = L2 (v + a F)           (HWE prior x GL)
 //   S  = w0 + w1 + w2 = L0 u + L2 v + (L0 F + 2 L1 (1-F) + L2 F) a
@@ -111,24 +119,30 @@ __device__ __forceinline__ void reciprocals(const double (&S)[K], double (&inv)[
   }
 }
 
-// One pass over a lane's K individuals at allele odds t = f/(1-f):
-// pn = sum (w1 + g w2)/S, pd = sum F w1/S.
+// One pass over a lane's K individuals at allele odds t = f/(1-f).  With x = 1/(S/u):
+//   X = sum (na + t nv) x      -> this pass adds t X to the running numerator,
+//   Z = sum (dz - t nv) x      -> and g + t Z to the running (denominator - numerator),  dz = da - na.
 template <int K>
-__device__ __forceinline__ void pass_sums(const double (&a0)[K], const double (&a2)[K], const double (&hh)[K],
-                                          const double (&na)[K], const double (&nv)[K], const double (&da)[K],
-                                          double t, double &pn, double &pd) {
-  double S[K], inv[K];
+__device__ __forceinline__ void pass_denominators(const double (&a0)[K], const double (&a2)[K], const double (&hh)[K],
+                                                  double t, double (&S)[K]) {
 #pragma unroll
   for (int k = 0; k < K; k++) S[k] = fma(fma(a2[k], t, hh[k]), t, a0[k]);
+}
+
+template <int K>
+__device__ __forceinline__ void pass_sums(const double (&S)[K], const double (&na)[K], const double (&nv)[K],
+                                          const double (&dz)[K], double t, double &X, double &Z) {
+  double inv[K];
   reciprocals<K>(S, inv);
   double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;   // two interleaved accumulator sets
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    if (k & 1) { B1 = fma(na[k], inv[k], B1); B2 = fma(nv[k], inv[k], B2); B3 = fma(da[k], inv[k], B3); }
-    else       { A1 = fma(na[k], inv[k], A1); A2 = fma(nv[k], inv[k], A2); A3 = fma(da[k], inv[k], A3); }
+    if (k & 1) { B1 = fma(na[k], inv[k], B1); B2 = fma(nv[k], inv[k], B2); B3 = fma(dz[k], inv[k], B3); }
+    else       { A1 = fma(na[k], inv[k], A1); A2 = fma(nv[k], inv[k], A2); A3 = fma(dz[k], inv[k], A3); }
   }
-  pn = t * fma(t, A2 + B2, A1 + B1);
-  pd = t * (A3 + B3);
+  const double s2 = A2 + B2;
+  X = fma(t, s2, A1 + B1);
+  Z = fma(-t, s2, A3 + B3);
 }
 
 // est_maf starts every site at f = 0.01 (gen_func.cpp:980)
@@ -156,43 +170,63 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
   e1 = fma(L0, u + a, L2 * (v + a));       // het prior is exp(-1e15) = 0 when F == 1
 }
 
+// Shared-memory layout of one site tile of freq_emission_warp: row r = plane * n_ind + i holds the
+// CTA's sites of individual i (planes: GL0, GL1, GL2, posterior).  Rows are padded so that the lanes
+// of a half-warp (different individuals, 1-4 neighbouring sites) fall into different banks.
+template <int G> struct FreqTile {
+  static constexpr int kSitesPerWarp = 32 / G;
+  static constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
+  static constexpr int kRowStride = kSitesPerCta + (G == 4 ? 4 : 2);   // doubles; multiple of 2 keeps TMA rows 16-byte aligned
+  static constexpr uint32_t kRowBytes = kSitesPerCta * sizeof(double);
+  __host__ __device__ static size_t tile_doubles(uint64_t n_ind) { return (size_t) 4 * n_ind * kRowStride; }
+  // per warp and individual: running product of e0 (mantissa in [1,2) as double + exponent as int)
+  __host__ __device__ static size_t acc_doubles(uint64_t n_ind_pad) { return (((size_t) (kFreqThreads / 32) * n_ind_pad * 3 / 2 + 15) / 16) * 16; }
+};
+
 // G lanes share one site (G divides 32); each lane keeps K individuals.
 //
 // PREFETCH: the CTA's next site tile (GL x3 + posterior rows of all individuals, 16-32 sites wide)
 // is fetched into shared memory by TMA bulk copies while the current tile runs its ~101 passes, so
 // the set-up of a tile reads shared memory instead of waiting on HBM (ncu r01c: long-scoreboard
 // stalls were 18 % of the kernel).  Two buffers, one mbarrier each.
+//
+// The pass loop is one dependency chain per site (sums -> lane reduction -> division -> next odds),
+// and a scheduler holds only two such warps, so the chain is kept as short as it can be: no
+// predication on it (converged sites simply keep iterating, their frequency was latched when they
+// stopped), the running (den - num) is accumulated directly so the next odds need one FMA and one
+// reciprocal after the reduction, and the stop test + vote hang off the side of the chain.
 template <int G, int K, bool PREFETCH, int OCC = freq_occupancy(K)>
 __global__ void __launch_bounds__(kFreqThreads, OCC)
 freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
-  constexpr int kSitesPerWarp = 32 / G;
-  constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
-  constexpr uint32_t kRowBytes = kSitesPerCta * sizeof(double);
+  using Tile = FreqTile<G>;
+  constexpr int kSitesPerWarp = Tile::kSitesPerWarp;
+  constexpr int kSitesPerCta = Tile::kSitesPerCta;
+  constexpr int kRowStride = Tile::kRowStride;
+  constexpr int kWarps = kFreqThreads / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane & (G - 1), sub = lane / G;
-  extern __shared__ __align__(128) double freq_smem[];     // [warps][n_ind_pad] log e0, then the tile buffers
-  double *loge0_acc = freq_smem;
-  for (unsigned i = threadIdx.x; i < (kFreqThreads / 32) * A.n_ind_pad; i += kFreqThreads) loge0_acc[i] = 0.0;
-  double *my_acc = loge0_acc + (size_t) warp * A.n_ind_pad;
+  extern __shared__ __align__(128) double freq_smem[];
+  double *mant_acc = freq_smem;                                              // [warps][n_ind_pad]
+  int *expo_acc = reinterpret_cast<int *>(freq_smem + (size_t) kWarps * A.n_ind_pad);   // [warps][n_ind_pad]
+  for (unsigned i = threadIdx.x; i < kWarps * A.n_ind_pad; i += kFreqThreads) { mant_acc[i] = 1.0; expo_acc[i] = 0; }
+  double *my_mant = mant_acc + (size_t) warp * A.n_ind_pad;
+  int *my_expo = expo_acc + (size_t) warp * A.n_ind_pad;
 
   // ---- prefetch machinery
   const unsigned n_planes = A.post ? 4u : 3u;
   const unsigned n_rows = n_planes * (unsigned) A.n_ind;
-  const size_t buf_doubles = (size_t) 4 * A.n_ind * kSitesPerCta;
-  const size_t acc_doubles = (((size_t) (kFreqThreads / 32) * A.n_ind_pad + 15) / 16) * 16;
-  double *bufs = freq_smem + acc_doubles;
+  const size_t buf_doubles = Tile::tile_doubles(A.n_ind);
+  double *bufs = freq_smem + Tile::acc_doubles(A.n_ind_pad);
   __shared__ alignas(8) uint64_t bars[2];
   auto issue_tile = [&](unsigned t, int b) {
-    // rows r = plane * n_ind + i: kSitesPerCta consecutive sites of individual i in that plane
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bars[b], n_rows * kRowBytes);
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bars[b], n_rows * Tile::kRowBytes);
     __syncthreads();
     const uint64_t first_site = (uint64_t) t * kSitesPerCta;
     for (unsigned r = threadIdx.x; r < n_rows; r += kFreqThreads) {
       const unsigned plane = r / (unsigned) A.n_ind, i = r - plane * (unsigned) A.n_ind;
       const double *src = (plane == 0 ? A.gl0 : plane == 1 ? A.gl1 : plane == 2 ? A.gl2 : A.post) +
                           (size_t) i * A.site_block + first_site;
-      tma_load_1d(bufs + (size_t) b * buf_doubles + ((size_t) plane * A.n_ind + i) * kSitesPerCta, src, kRowBytes,
-                  &bars[b]);
+      tma_load_1d(bufs + (size_t) b * buf_doubles + (size_t) r * kRowStride, src, Tile::kRowBytes, &bars[b]);
     }
   };
   if (PREFETCH) {
@@ -208,12 +242,13 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
     const double *tile_buf = bufs + (size_t) (round & 1) * buf_doubles;
+    const size_t plane = (size_t) A.n_ind * kRowStride;
     if (PREFETCH) {
       if (tile + gridDim.x < n_site_tiles) issue_tile(tile + gridDim.x, (round & 1) ^ 1);
       mbar_wait(&bars[round & 1], (round >> 1) & 1);
     }
 
-    double a0[K], a2[K], hh[K], na[K], nv[K], da[K];
+    double a0[K], a2[K], hh[K], na[K], nv[K], dz[K];
     double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -222,8 +257,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       if (i < A.n_ind) {
         double L0, L1, L2, F;
         if (PREFETCH) {
-          const double *row = tile_buf + i * kSitesPerCta + site_in_cta;
-          const size_t plane = (size_t) A.n_ind * kSitesPerCta;
+          const double *row = tile_buf + i * kRowStride + site_in_cta;
           L0 = row[0]; L1 = row[plane]; L2 = row[2 * plane];
           F = A.post ? row[3 * plane] : 0.0;
           if (!site_ok) { L0 = 1.0 / 3; L1 = 1.0 / 3; L2 = 1.0 / 3; F = 0.0; }   // padding sites: harmless values
@@ -236,7 +270,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       } else {
         c = null_coef();
       }
-      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; da[k] = c.da;
+      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; dz[k] = c.da - c.na;
       g_sum += c.g;
     }
 
@@ -244,28 +278,34 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
     if (A.update_freq) {
 #pragma unroll
       for (int m = 1; m < G; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
-      double num = 0.0, den = 0.0, odds = kStartOdds;
+      double num = 0.0, dmn_next = g_sum;     // running numerator; running (den - num) + this pass's sum of g
+      double odds = kStartOdds, prev = kStartFreq;
       bool active = site_ok;
       int passes = 0;
-      while (__any_sync(kFull, active)) {
-        double pn, pd;
-        pass_sums<K>(a0, a2, hh, na, nv, da, odds, pn, pd);
+      double S[K];
+      pass_denominators<K>(a0, a2, hh, odds, S);
+      do {
+        double X, Z;
+        pass_sums<K>(S, na, nv, dz, odds, X, Z);
 #pragma unroll
         for (int m = 1; m < G; m <<= 1) {
-          pn += __shfl_xor_sync(kFull, pn, m);
-          pd += __shfl_xor_sync(kFull, pd, m);
+          X += __shfl_xor_sync(kFull, X, m);
+          Z += __shfl_xor_sync(kFull, Z, m);
         }
-        pd += g_sum;
+        num = fma(odds, X, num);
+        const double dmn = fma(odds, Z, dmn_next);
+        odds = num * rcp_pos(dmn);
+        // the next pass starts here, inside the same basic block, so that the compiler schedules the
+        // chain num -> odds -> S ahead of the stop test (one wasted set of denominators at the exit)
+        pass_denominators<K>(a0, a2, hh, odds, S);
+        dmn_next = dmn + g_sum;
+        const double now = num * rcp_pos<true>(num + dmn);   // frequency after this pass: off the chain
         passes++;
-        if (active) {
-          num += pn; den += pd;
-          const double before = freq;
-          odds = num * rcp_pos<true>(den - num);        // feeds the next pass
-          freq = num * rcp_pos<true>(den);              // independent of it: only the stop test waits
-          // do { ... } while (|before - freq| > EPSILON && iters++ < 100)   gen_func.cpp:1006
-          active = (fabs(before - freq) > kEps) && (passes <= 100);
-        }
-      }
+        freq = active ? now : freq;
+        // do { ... } while (|before - freq| > EPSILON && iters++ < 100)   gen_func.cpp:1006
+        active = active && (fabs(prev - now) > kEps) && (passes <= 100);
+        prev = now;
+      } while (__any_sync(kFull, active));
       if (site_ok && grp == 0) A.freq[site] = freq;
     }
 
@@ -273,29 +313,35 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
-      double le0 = 0.0;
+      double pe0 = 1.0;
       if (i < A.n_ind && site_ok) {
         const size_t at = (size_t) i * A.site_block + site;
-        const double L1 = PREFETCH ? tile_buf[((size_t) A.n_ind + i) * kSitesPerCta + site_in_cta] : A.gl1[at];
+        const double L1 = PREFETCH ? tile_buf[plane + i * kRowStride + site_in_cta] : A.gl1[at];
         double e0, e1;
         emissions(a0[k], L1, a2[k], freq, e0, e1);
         *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
         if (A.e0) A.e0[at] = e0;
-        le0 = log(e0);
+        pe0 = e0;
       }
-      // sum over the warp's sites (lanes with equal grp), fixed order
+      // sum of log e0 over sites = log of the running product: multiply the warp's sites (lanes with
+      // equal grp, fixed order), then fold into the warp's (mantissa, exponent) accumulator
 #pragma unroll
-      for (int m = G; m < 32; m <<= 1) le0 += __shfl_xor_sync(kFull, le0, m);
-      if (sub == 0 && i < A.n_ind_pad) my_acc[i] += le0;
+      for (int m = G; m < 32; m <<= 1) pe0 *= __shfl_xor_sync(kFull, pe0, m);
+      if (sub == 0 && i < A.n_ind_pad) {
+        int e;
+        my_mant[i] = split_exponent(my_mant[i] * pe0, e);
+        my_expo[i] += e;
+      }
     }
     if (PREFETCH) __syncthreads();            // the buffer is refilled two tiles from now
   }
   __syncthreads();
   for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kFreqThreads) {
-    double s = 0.0;
+    double m = 1.0;
+    int e = 0;
 #pragma unroll
-    for (int w = 0; w < kFreqThreads / 32; w++) s += loge0_acc[(size_t) w * A.n_ind_pad + i];
-    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = s;
+    for (int w = 0; w < kWarps; w++) { m *= mant_acc[(size_t) w * A.n_ind_pad + i]; e += expo_acc[(size_t) w * A.n_ind_pad + i]; }
+    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = fma((double) e, 0.6931471805599453, log(m));
   }
 }
 
@@ -331,7 +377,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
 
-    double a0[K], a2[K], hh[K], na[K], nv[K], da[K];
+    double a0[K], a2[K], hh[K], na[K], nv[K], dz[K];
     double g_sum = 0.0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -344,7 +390,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
       } else {
         c = null_coef();
       }
-      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; da[k] = c.da;
+      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; dz[k] = c.da - c.na;
       g_sum += c.g;
     }
 
@@ -358,28 +404,31 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
 #pragma unroll
       for (int w = 0; w < W; w++) g_sum += gpart[team][w];
 
-      double num = 0.0, den = 0.0, odds = kStartOdds;
+      double num = 0.0, dmn_next = g_sum, odds = kStartOdds;
       bool active = site_ok;                            // identical in every thread of the team
       int passes = 0;
       while (active) {
-        double pn, pd;
-        pass_sums<K>(a0, a2, hh, na, nv, da, odds, pn, pd);
+        double X, Z, S[K];
+        pass_denominators<K>(a0, a2, hh, odds, S);
+        pass_sums<K>(S, na, nv, dz, odds, X, Z);
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) {
-          pn += __shfl_xor_sync(kFull, pn, m);
-          pd += __shfl_xor_sync(kFull, pd, m);
+          X += __shfl_xor_sync(kFull, X, m);
+          Z += __shfl_xor_sync(kFull, Z, m);
         }
         const int buf = passes & 1;
-        if (lane == 0) part[buf][team][wt] = make_double2(pn, pd);
+        if (lane == 0) part[buf][team][wt] = make_double2(X, Z);
         team_barrier(team, G);
-        pn = 0.0; pd = g_sum;
+        X = 0.0; Z = 0.0;
 #pragma unroll
-        for (int w = 0; w < W; w++) { const double2 q = part[buf][team][w]; pn += q.x; pd += q.y; }
+        for (int w = 0; w < W; w++) { const double2 q = part[buf][team][w]; X += q.x; Z += q.y; }
         passes++;
-        num += pn; den += pd;
+        num = fma(odds, X, num);
+        const double dmn = fma(odds, Z, dmn_next);
+        odds = num * rcp_pos(dmn);
+        dmn_next = dmn + g_sum;
         const double before = freq;
-        odds = num * rcp_pos<true>(den - num);
-        freq = num * rcp_pos<true>(den);
+        freq = num * rcp_pos<true>(num + dmn);
         active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
       }
       if (site_ok && grp == 0) A.freq[site] = freq;
@@ -586,10 +635,10 @@ unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
 
 template <int G, int K>
 static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
+  const unsigned per_cta = FreqTile<G>::kSitesPerCta;
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
-  const size_t acc = ((((size_t) (kFreqThreads / 32) * a.n_ind_pad + 15) / 16) * 16) * sizeof(double);
-  const size_t bufs = (size_t) 2 * 4 * a.n_ind * per_cta * sizeof(double);
+  const size_t acc = FreqTile<G>::acc_doubles(a.n_ind_pad) * sizeof(double);
+  const size_t bufs = 2 * FreqTile<G>::tile_doubles(a.n_ind) * sizeof(double);
   // all resident CTAs of an SM must fit their double buffers in its 227 KB of shared memory (1 KB reserved each)
   const size_t smem_cap = (size_t) 227 * 1024 / freq_occupancy(K) - 2048;
   const bool prefetch = acc + bufs <= smem_cap && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
