@@ -171,14 +171,16 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
 }
 
 // Shared-memory layout of one site tile of freq_emission_warp: row r = plane * n_ind + i holds the
-// CTA's sites of individual i (planes: GL0, GL1, GL2, posterior).  Rows are padded so that the lanes
-// of a half-warp (different individuals, 1-4 neighbouring sites) fall into different banks.
+// CTA's sites of individual i (planes: GL0, GL1, GL2, posterior).  Rows are skewed by 16 bytes (the
+// TMA alignment) every 2^skew rows so that the lanes of a half-warp (different individuals, 1-4
+// neighbouring sites) spread over the banks: skew 0 is conflict-free, 1 two-way, ... 31 no padding.
 template <int G> struct FreqTile {
   static constexpr int kSitesPerWarp = 32 / G;
   static constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
-  static constexpr int kRowStride = kSitesPerCta + (G == 4 ? 4 : 2);   // doubles; multiple of 2 keeps TMA rows 16-byte aligned
+  static constexpr int kPad = G == 4 ? 4 : 2;                          // doubles
   static constexpr uint32_t kRowBytes = kSitesPerCta * sizeof(double);
-  __host__ __device__ static size_t tile_doubles(uint64_t n_ind) { return (size_t) 4 * n_ind * kRowStride; }
+  __host__ __device__ static size_t row_offset(size_t r, int skew) { return r * kSitesPerCta + kPad * (r >> skew); }
+  __host__ __device__ static size_t tile_doubles(uint64_t n_ind, int skew) { return row_offset(4 * n_ind, skew) + kPad; }
   // per warp and individual: running product of e0 (mantissa in [1,2) as double + exponent as int)
   __host__ __device__ static size_t acc_doubles(uint64_t n_ind_pad) { return (((size_t) (kFreqThreads / 32) * n_ind_pad * 3 / 2 + 15) / 16) * 16; }
 };
@@ -197,11 +199,10 @@ template <int G> struct FreqTile {
 // reciprocal after the reduction, and the stop test + vote hang off the side of the chain.
 template <int G, int K, bool PREFETCH, int OCC = freq_occupancy(K)>
 __global__ void __launch_bounds__(kFreqThreads, OCC)
-freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
+freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
   using Tile = FreqTile<G>;
   constexpr int kSitesPerWarp = Tile::kSitesPerWarp;
   constexpr int kSitesPerCta = Tile::kSitesPerCta;
-  constexpr int kRowStride = Tile::kRowStride;
   constexpr int kWarps = kFreqThreads / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane & (G - 1), sub = lane / G;
@@ -215,7 +216,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
   // ---- prefetch machinery
   const unsigned n_planes = A.post ? 4u : 3u;
   const unsigned n_rows = n_planes * (unsigned) A.n_ind;
-  const size_t buf_doubles = Tile::tile_doubles(A.n_ind);
+  const size_t buf_doubles = Tile::tile_doubles(A.n_ind, skew);
   double *bufs = freq_smem + Tile::acc_doubles(A.n_ind_pad);
   __shared__ alignas(8) uint64_t bars[2];
   auto issue_tile = [&](unsigned t, int b) {
@@ -226,7 +227,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       const unsigned plane = r / (unsigned) A.n_ind, i = r - plane * (unsigned) A.n_ind;
       const double *src = (plane == 0 ? A.gl0 : plane == 1 ? A.gl1 : plane == 2 ? A.gl2 : A.post) +
                           (size_t) i * A.site_block + first_site;
-      tma_load_1d(bufs + (size_t) b * buf_doubles + (size_t) r * kRowStride, src, Tile::kRowBytes, &bars[b]);
+      tma_load_1d(bufs + (size_t) b * buf_doubles + Tile::row_offset(r, skew), src, Tile::kRowBytes, &bars[b]);
     }
   };
   if (PREFETCH) {
@@ -242,7 +243,6 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
     const double *tile_buf = bufs + (size_t) (round & 1) * buf_doubles;
-    const size_t plane = (size_t) A.n_ind * kRowStride;
     if (PREFETCH) {
       if (tile + gridDim.x < n_site_tiles) issue_tile(tile + gridDim.x, (round & 1) ^ 1);
       mbar_wait(&bars[round & 1], (round >> 1) & 1);
@@ -257,9 +257,11 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       if (i < A.n_ind) {
         double L0, L1, L2, F;
         if (PREFETCH) {
-          const double *row = tile_buf + i * kRowStride + site_in_cta;
-          L0 = row[0]; L1 = row[plane]; L2 = row[2 * plane];
-          F = A.post ? row[3 * plane] : 0.0;
+          const double *at = tile_buf + site_in_cta;
+          L0 = at[Tile::row_offset(i, skew)];
+          L1 = at[Tile::row_offset(A.n_ind + i, skew)];
+          L2 = at[Tile::row_offset(2 * A.n_ind + i, skew)];
+          F = A.post ? at[Tile::row_offset(3 * A.n_ind + i, skew)] : 0.0;
           if (!site_ok) { L0 = 1.0 / 3; L1 = 1.0 / 3; L2 = 1.0 / 3; F = 0.0; }   // padding sites: harmless values
         } else {
           const size_t at = (size_t) i * A.site_block + sl;
@@ -316,7 +318,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles) {
       double pe0 = 1.0;
       if (i < A.n_ind && site_ok) {
         const size_t at = (size_t) i * A.site_block + site;
-        const double L1 = PREFETCH ? tile_buf[plane + i * kRowStride + site_in_cta] : A.gl1[at];
+        const double L1 = PREFETCH ? tile_buf[Tile::row_offset(A.n_ind + i, skew) + site_in_cta] : A.gl1[at];
         double e0, e1;
         emissions(a0[k], L1, a2[k], freq, e0, e1);
         *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
@@ -638,22 +640,24 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   const unsigned per_cta = FreqTile<G>::kSitesPerCta;
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t acc = FreqTile<G>::acc_doubles(a.n_ind_pad) * sizeof(double);
-  const size_t bufs = 2 * FreqTile<G>::tile_doubles(a.n_ind) * sizeof(double);
-  // all resident CTAs of an SM must fit their double buffers in its 227 KB of shared memory (1 KB reserved each)
-  const size_t smem_cap = (size_t) 227 * 1024 / freq_occupancy(K) - 2048;
-  const bool prefetch = acc + bufs <= smem_cap && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
+  // all resident CTAs of an SM must fit their double buffers in its 228 KB of shared memory (1 KB reserved each);
+  // take the least conflicting row skew that fits
+  const size_t smem_cap = (size_t) 228 * 1024 / freq_occupancy(K) - 1024 - 256;
+  int skew = 0;
+  size_t bufs = 0;
+  bool prefetch = false;
+  for (int sk : {0, 1, 2, 31}) {
+    bufs = 2 * FreqTile<G>::tile_doubles(a.n_ind, sk) * sizeof(double);
+    if (acc + bufs <= smem_cap) { skew = sk; prefetch = true; break; }
+  }
+  if (getenv("NFH_FREQ_NO_PREFETCH")) prefetch = false;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
     attr_done = true;
   }
-  if (G == 16 && K == 7 && getenv("NFH_FREQ_OCC4")) {   // experiment: 128-register build, four CTAs per SM
-    cudaFuncSetAttribute(freq_emission_warp<16, 7, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
-    freq_emission_warp<16, 7, true, 4><<<grid * 4 / 3, kFreqThreads, acc + bufs, st>>>(a, tiles);
-    return;
-  }
-  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
-  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles);
+  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles, skew);
+  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles, 31);
 }
 
 template <int W, int K>
