@@ -38,8 +38,8 @@ N_SITES = 1_000_000
 START_FREQ, START_F, START_ALPHA = 0.1, 0.1, 0.2
 # algorithmic work per unit, stated in DESIGN.md "Measurement"
 ESTEP_BYTES_PER_IND_SITE = 24.0          # read 2 emissions, write 1 posterior
-FREQ_FLOPS_PER_IND_PASS = 15.0           # linear-space est_maf contribution: 9 FP64 instructions (6 of them FMA)
-FREQ_PASSES = 101.0                      # upper bound per site (gen_func.cpp:1006); ~90% of sites hit it
+FREQ_FLOPS_PER_IND_PASS = 13.75          # odds-form est_maf contribution: 8 FP64 instructions (5.75 of them FMA)
+FREQ_INSTR_PER_IND_PASS = 8.0            # -> at most 13.75/16 of the DFMA peak; passes per site are counted by the kernel
 LKL_FLOPS_PER_IND_SITE_POINT = 14.0      # factored 2x2 update: 2 ADD + 4 FMA + 4 MUL per objective point and site
 EXP_FLOPS = 21.0                         # kappa = expm1(alpha d): 13 FP64 instructions, 8 of them FMA; 3 per 5 points
 
@@ -59,51 +59,89 @@ def parse_args():
 
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / power / throttle reasons sampled DURING the timed regions (B200_PROFILING.md): NVML every
+    10 ms when pynvml is importable, else `nvidia-smi -lms 100`."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, uuid=None):
+        self.rows, self.proc, self.index, self.uuid = [], None, index, uuid
+        self.nvml, self.handle, self.stop_flag, self.t = None, None, threading.Event(), None
+        self.sm, self.mx, self.pw, self.reasons = [], [], [], set()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid
+                           else pynvml.nvmlDeviceGetHandleByIndex(self.index))
+            self.nvml = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.pw.append(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in bits.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.01)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        if self.nvml:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+        elif self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+            for r in self.rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    self.sm.append(float(f[0])); self.mx.append(float(f[1])); self.pw.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(self.NAMES, f[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm),
+                "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(self.reasons)}
 
 
 def ncu_traffic():
@@ -233,11 +271,16 @@ def main():
     # ---- device-timed region: K successive EM iterations, state resident in HBM
     ctx.timing(True)
     ctx.timing_read(reset=True)
+    ctx.freq_passes(reset=True)
     launches0 = ctx.kernel_launches
     evals0, rounds0 = runner.total_evals, runner.total_rounds
     ext = torch.cuda.ExternalStream(ctx.stream)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:  # noqa: BLE001
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     barrier()
     if rank == 0:
         sampler.start()
@@ -249,6 +292,7 @@ def main():
     barrier()
     dev_ms = e0.elapsed_time(e1)
     fam = ctx.timing_read(reset=True)
+    site_passes = ctx.freq_passes(reset=True)      # rank 0's sites, all K steps
     ctx.timing(False)
     launches = ctx.kernel_launches - launches0
     evals, rounds = runner.total_evals - evals0, runner.total_rounds - rounds0
@@ -286,7 +330,8 @@ def main():
         rank_units = float(n_own) * S                       # recursion-side units of this rank per step
         freq_units = float(N_total) * ctx.sites_owned       # frequency-side units of this rank per step
         estep_gbs = ESTEP_BYTES_PER_IND_SITE * rank_units / (per_step["estep"] * 1e-3) / 1e9
-        freq_tf = FREQ_FLOPS_PER_IND_PASS * FREQ_PASSES * freq_units / (per_step["freq"] * 1e-3) / 1e12
+        passes_per_site = site_passes / max(ctx.sites_owned * args.steps, 1)
+        freq_tf = FREQ_FLOPS_PER_IND_PASS * passes_per_site * freq_units / (per_step["freq"] * 1e-3) / 1e12
         evals_step = evals / args.steps
         lkl_flops = (LKL_FLOPS_PER_IND_SITE_POINT + 0.6 * EXP_FLOPS) * evals_step * S
         lkl_tf = lkl_flops / (per_step["lkl_batch"] * 1e-3) / 1e12 if per_step["lkl_batch"] > 0 else 0.0
@@ -300,7 +345,10 @@ def main():
                       "peak_source": peak_src, "ms_per_step": per_step["estep"]}
         roof_freq = {"kernel": "freq_emission_warp", "bound": "fp64", "achieved": freq_tf,
                      "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": freq_tf / (fp64_peak / 1e12),
-                     "traffic": t_freq, "instruction_mix_ceiling": 15.0 / 18.0, "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
+                     "traffic": t_freq, "passes_per_site": passes_per_site,
+                     "instruction_mix_ceiling": FREQ_FLOPS_PER_IND_PASS / (2 * FREQ_INSTR_PER_IND_PASS),
+                     "operand_fetch_note": "DFMA with 3 register operands issues every 3.06 cycles, not 2 "
+                                           "(profiles/microbench/fp64_operands.cu)", "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
                      "ms_per_step": per_step["freq"]}
         roof_lkl = {"kernel": "lkl_tile_products", "bound": "fp64", "achieved": lkl_tf, "peak": fp64_peak / 1e12,
                     "unit": "TFLOP/s", "frac": lkl_tf / (fp64_peak / 1e12), "traffic": t_lkl,

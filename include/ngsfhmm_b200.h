@@ -172,6 +172,9 @@ int nfh_probe_fp64(nfh_ctx *ctx, double *flops_per_s);
  * [3]=viterbi [4]=emission.  Enabled by nfh_timing(ctx, 1). */
 int nfh_timing(nfh_ctx *ctx, int enable);
 int nfh_timing_read(nfh_ctx *ctx, double ms_out[8], uint64_t launches_out[8], int reset);
+/* Sum over this rank's sites of the est_maf passes each site ran (<= 101, gen_func.cpp:1006) in all
+ * nfh_freq_update calls since the last reset: the pass count behind bench.py's FP64 work figure. */
+int nfh_freq_passes(nfh_ctx *ctx, uint64_t *total, int reset);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "nfh_upload_gl", "nfh_upload_pos_dist", "nfh_set_freq", "nfh_get_freq", "nfh_set_ind_params",
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
-    "nfh_timing_read",
+    "nfh_timing_read", "nfh_freq_passes",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library():
     L.nfh_probe_fp64.restype = cint; L.nfh_probe_fp64.argtypes = [_vp, _dp]
     L.nfh_timing.restype = cint; L.nfh_timing.argtypes = [_vp, cint]
     L.nfh_timing_read.restype = cint; L.nfh_timing_read.argtypes = [_vp, _dp, C.POINTER(u64), cint]
+    L.nfh_freq_passes.restype = cint; L.nfh_freq_passes.argtypes = [_vp, C.POINTER(u64), cint]
     _lib = L
     return L
 
@@ -266,3 +267,9 @@ class Context:
         ms = np.zeros(8); n = np.zeros(8, dtype=np.uint64)
         self._chk(self.L.nfh_timing_read(self.h, _p(ms), n.ctypes.data_as(C.POINTER(C.c_uint64)), int(reset)))
         return {TIMING_FAMILIES[i]: (float(ms[i]), int(n[i])) for i in range(6)}
+
+    def freq_passes(self, reset=True):
+        """Sum over this rank's sites of the est_maf passes run since the last reset."""
+        v = C.c_uint64()
+        self._chk(self.L.nfh_freq_passes(self.h, C.byref(v), int(reset)))
+        return int(v.value)

@@ -237,6 +237,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
   if (PREFETCH && blockIdx.x < n_site_tiles) issue_tile(blockIdx.x, 0);
 
   unsigned round = 0;
+  unsigned my_passes = 0;                       // passes of the sites this lane reports (grp == 0)
   for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x, round++) {
     const int site_in_cta = warp * kSitesPerWarp + sub;
     const uint64_t site = (uint64_t) tile * kSitesPerCta + site_in_cta;
@@ -283,7 +284,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
       double num = 0.0, dmn_next = g_sum;     // running numerator; running (den - num) + this pass's sum of g
       double odds = kStartOdds, prev = kStartFreq;
       bool active = site_ok;
-      int passes = 0;
+      int passes = 0, site_passes = 0;
       double S[K];
       pass_denominators<K>(a0, a2, hh, odds, S);
       do {
@@ -304,11 +305,12 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
         const double now = num * rcp_pos<true>(num + dmn);   // frequency after this pass: off the chain
         passes++;
         freq = active ? now : freq;
+        site_passes = active ? passes : site_passes;
         // do { ... } while (|before - freq| > EPSILON && iters++ < 100)   gen_func.cpp:1006
         active = active && (fabs(prev - now) > kEps) && (passes <= 100);
         prev = now;
       } while (__any_sync(kFull, active));
-      if (site_ok && grp == 0) A.freq[site] = freq;
+      if (site_ok && grp == 0) { A.freq[site] = freq; my_passes += site_passes; }
     }
 
     // emission refresh from the same site (L1 is re-read: the coefficients fold it with F)
@@ -338,6 +340,9 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
     if (PREFETCH) __syncthreads();            // the buffer is refilled two tiles from now
   }
   __syncthreads();
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) my_passes += __shfl_xor_sync(kFull, my_passes, m);
+  if (lane == 0 && my_passes) atomicAdd(A.pass_total, (unsigned long long) my_passes);
   for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kFreqThreads) {
     double m = 1.0;
     int e = 0;
@@ -433,7 +438,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         freq = num * rcp_pos<true>(num + dmn);
         active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
       }
-      if (site_ok && grp == 0) A.freq[site] = freq;
+      if (site_ok && grp == 0) { A.freq[site] = freq; atomicAdd(A.pass_total, (unsigned long long) passes); }
       team_barrier(team, G);                            // gpart / part are reused by the next tile
     }
 
@@ -486,6 +491,7 @@ freq_emission_stream(FreqArgs A) {
         freq = num / den;
       } while (fabs(before - freq) > kEps && passes++ < 100);
       A.freq[site] = freq;
+      atomicAdd(A.pass_total, (unsigned long long) min(passes + 1, 101));
     }
     for (uint64_t i = 0; i < A.n_ind; i++) {
       const size_t at = (size_t) i * A.site_block + site;

@@ -67,6 +67,7 @@ struct FreqArgs {
   double *e0;                     // out: e0 or NULL
   PeerWindows emis_peers;         // destination of row i = owner of individual i
   double *loge0_part;             // out: [gridDim.x][n_ind_pad] partial sums of log e0
+  unsigned long long *pass_total; // += sum over sites of the est_maf passes each site needed (bench.py's flop count)
   uint64_t n_ind, n_ind_pad, site_block, sites_owned;
   int update_freq;                // 1: run est_maf; 0: keep freq
 };

@@ -92,11 +92,17 @@ double orc_calc_emission(const double gl[3], double maf, int k) {
 /* gen_func.cpp:974-1009.  Note num/den are NOT reset between passes and the
  * start value is always 0.01 (SURVEY.md finding 2). */
 double orc_est_maf(uint64_t n_ind, const double *gl, const double *indF) {
-  int passes = 0;
+  return orc_est_maf_counted(n_ind, gl, indF, NULL);
+}
+
+/* Same loop; *n_passes = number of times the body ran (1..101). */
+double orc_est_maf_counted(uint64_t n_ind, const double *gl, const double *indF, int *n_passes) {
+  int passes = 0, ran = 0;
   double num = 0, den = 0, freq = 0.01, before;
   double prior[3], pp[3];
   do {
     before = freq;
+    ran++;
     for (uint64_t i = 0; i < n_ind; i++) {
       double F = indF[i];
       orc_calc_HWE(prior, freq, F, 1);
@@ -107,6 +113,7 @@ double orc_est_maf(uint64_t n_ind, const double *gl, const double *indF) {
     }
     freq = num / den;
   } while (REF_ABS(before - freq) > ORC_EPSILON && passes++ < 100);
+  if (n_passes) *n_passes = ran;
   return freq;
 }
 

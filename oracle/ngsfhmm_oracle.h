@@ -40,6 +40,7 @@ void orc_post_prob(double pp[3], const double lkl[3], const double *prior);
 double orc_calc_emission(const double gl[3], double maf, int k);
 /* gen_func.cpp:974-1009; gl is n_ind x 3 (log, normalised) */
 double orc_est_maf(uint64_t n_ind, const double *gl, const double *indF);
+double orc_est_maf_counted(uint64_t n_ind, const double *gl, const double *indF, int *n_passes);
 
 /* HMM.cpp:6-28.  e_prob: S x 2 log emissions; dist: S (Mb, +inf allowed).
  * Fw: (S+1) x 2 or NULL.  Returns logsum(Fw[S]); NaN if a NaN term appears

@@ -1,2 +1,9 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -3
-timeout 600 python bench.py --steps 4 --warmup 3 --no_cpu_baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['ms_per_step'], d['kernel_ms_per_step'], d['final_loglkl_rank0'], d['e2e']['ms_per_step'])"
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 900 python bench.py > gpurun_out/bench_r01f_full.json 2> gpurun_out/bench_r01f.err; tail -c 600 gpurun_out/bench_r01f.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r01f_full.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['value'], d['kernel_ms_per_step'])
+print(d['roofline'])
+print(d['e2e'], d['cpu_baseline'], d['clocks'])
+PY

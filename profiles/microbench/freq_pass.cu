@@ -113,12 +113,16 @@ __global__ void __launch_bounds__(256, 1) pingpong(const double *coef, double *o
   if (SYNC == 1 && role == 1) { const long long t0 = clock64(); while (clock64() - t0 < delay) {} }
   if (SYNC >= 2 && role == 1) bar_arrive(theirs, 64);       // role 0 goes first
   while (p < passes) {
-    if (SYNC >= 2) bar_sync(mine, 64);
+    if (SYNC >= 2) { bar_sync(mine, 64); asm volatile("" : "+d"(odds)); }   // the body may not start before the barrier
     double S[K], inv[K];
 #pragma unroll
     for (int k = 0; k < K; k++) S[k] = fma(fma(a2[k], odds, hh[k]), odds, a0[k]);
     reciprocals<K>(S, inv);
-    if (SYNC == 3 && !(role == 1 && p == passes - 1)) bar_arrive(theirs, 64);
+    if (SYNC == 3) {
+#pragma unroll
+      for (int k = 0; k < K; k++) asm volatile("" : "+d"(inv[k]));
+      if (!(role == 1 && p == passes - 1)) bar_arrive(theirs, 64);
+    }
     double A1 = 0, A2 = 0, A3 = 0, B1 = 0, B2 = 0, B3 = 0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -126,7 +130,10 @@ __global__ void __launch_bounds__(256, 1) pingpong(const double *coef, double *o
       else { A1 = fma(na[k], inv[k], A1); A2 = fma(nv[k], inv[k], A2); A3 = fma(da[k], inv[k], A3); }
     }
     double pn = odds * fma(odds, A2 + B2, A1 + B1), pd = odds * (A3 + B3);
-    if (SYNC == 2 && !(role == 1 && p == passes - 1)) bar_arrive(theirs, 64);
+    if (SYNC == 2) {
+      asm volatile("" : "+d"(pn), "+d"(pd));                              // the body is issued before the hand-over
+      if (!(role == 1 && p == passes - 1)) bar_arrive(theirs, 64);
+    }
 #pragma unroll
     for (int m = 1; m < G; m <<= 1) { pn += __shfl_xor_sync(0xffffffffu, pn, m); pd += __shfl_xor_sync(0xffffffffu, pd, m); }
     pd += 150.0;

@@ -58,6 +58,8 @@ class Oracle:
         L.orc_calc_emission.argtypes = [_dp, C.c_double, C.c_int]
         L.orc_est_maf.restype = C.c_double
         L.orc_est_maf.argtypes = [C.c_uint64, _dp, _dp]
+        L.orc_est_maf_counted.restype = C.c_double
+        L.orc_est_maf_counted.argtypes = [C.c_uint64, _dp, _dp, C.POINTER(C.c_int)]
         for name in ("orc_forward", "orc_backward"):
             fn = getattr(L, name)
             fn.restype = C.c_double
@@ -81,6 +83,13 @@ class Oracle:
     def est_maf(self, gl, indF):
         g = f64(gl); F = f64(indF)
         return self.lib.orc_est_maf(len(F), _d(g), _d(F))
+
+    def est_maf_counted(self, gl, indF):
+        """(freq, passes) of one site."""
+        g = f64(gl); F = f64(indF)
+        n = C.c_int(0)
+        f = self.lib.orc_est_maf_counted(len(F), _d(g), _d(F), C.byref(n))
+        return f, n.value
 
     def calc_HWE(self, maf, F, log_scale=True):
         out = np.empty(3)

@@ -141,6 +141,24 @@ def test_freq_update_large_n_variants(oracle, N, S):
         np.testing.assert_allclose(lk2, lk2_o, rtol=LKL_RTOL)
 
 
+def test_freq_pass_counter_matches_oracle(oracle):
+    """nfh_freq_passes (the work figure behind bench.py's roofline) = the oracle's est_maf pass counts."""
+    d, ctx = _setup(20, 500, 77, freq=(0.02, 0.5), indF=(0.0, 0.5))
+    with ctx:
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.1, 0.1, 0.2)
+        ctx.estep(); post = ctx.get_posterior()
+        ctx.freq_passes(reset=True)
+        f_new = ctx.freq_update(1)
+        total = ctx.freq_passes(reset=True)
+        want = 0
+        for s in range(d.n_sites):
+            f_o, n = oracle.est_maf_counted(gl_ind[:, s, :], post[:, s])
+            want += n
+            assert abs(f_o - f_new[s]) < 1e-11
+        assert total == want
+        assert ctx.freq_passes() == 0
+
+
 def test_freq_init_estimate_with_zero_posterior(oracle):
     """--freq e: est_maf with scalar F = 0 (parse_args.cpp:316-318)."""
     N, S = 10, 1500
