@@ -249,30 +249,32 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
       mbar_wait(&bars[round & 1], (round >> 1) & 1);
     }
 
+    // all loads of the tile are issued before the first coefficient is formed; the coefficient
+    // arrays double as staging for L0, L2, L1, F
     double a0[K], a2[K], hh[K], na[K], nv[K], dz[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      const uint64_t il = i < A.n_ind ? i : 0;
+      if (PREFETCH) {
+        const double *at = tile_buf + site_in_cta;
+        a0[k] = at[Tile::row_offset(il, skew)];
+        hh[k] = at[Tile::row_offset(A.n_ind + il, skew)];
+        a2[k] = at[Tile::row_offset(2 * A.n_ind + il, skew)];
+        na[k] = A.post ? at[Tile::row_offset(3 * A.n_ind + il, skew)] : 0.0;
+      } else {
+        const size_t at = (size_t) il * A.site_block + sl;
+        a0[k] = A.gl0[at]; hh[k] = A.gl1[at]; a2[k] = A.gl2[at];
+        na[k] = A.post ? A.post[at] : 0.0;
+      }
+    }
     double g_sum = 0.0;                       // sum over individuals of (2 - F): constant part of den per pass
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
-      IndCoef c;
-      if (i < A.n_ind) {
-        double L0, L1, L2, F;
-        if (PREFETCH) {
-          const double *at = tile_buf + site_in_cta;
-          L0 = at[Tile::row_offset(i, skew)];
-          L1 = at[Tile::row_offset(A.n_ind + i, skew)];
-          L2 = at[Tile::row_offset(2 * A.n_ind + i, skew)];
-          F = A.post ? at[Tile::row_offset(3 * A.n_ind + i, skew)] : 0.0;
-          if (!site_ok) { L0 = 1.0 / 3; L1 = 1.0 / 3; L2 = 1.0 / 3; F = 0.0; }   // padding sites: harmless values
-        } else {
-          const size_t at = (size_t) i * A.site_block + sl;
-          L0 = A.gl0[at]; L1 = A.gl1[at]; L2 = A.gl2[at];
-          F = A.post ? A.post[at] : 0.0;
-        }
-        c = make_coef(L0, L1, L2, F);
-      } else {
-        c = null_coef();
-      }
+      double L0 = a0[k], L1 = hh[k], L2 = a2[k], F = na[k];
+      if (PREFETCH && !site_ok) { L0 = 1.0 / 3; L1 = 1.0 / 3; L2 = 1.0 / 3; F = 0.0; }   // padding sites: harmless values
+      const IndCoef c = i < A.n_ind ? make_coef(L0, L1, L2, F) : null_coef();
       a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; dz[k] = c.da - c.na;
       g_sum += c.g;
     }
@@ -372,31 +374,38 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / W, wt = warp % W;
   const int grp = wt * 32 + lane;
-  extern __shared__ double team_smem[];                 // [kTeams][n_ind_pad] log e0 accumulators
+  // per (team, individual): running product of e0 as mantissa in [1,2) + exponent (see freq_emission_warp)
+  extern __shared__ __align__(16) double team_smem[];
+  double *mant_acc = team_smem;                                                        // [kTeams][n_ind_pad]
+  int *expo_acc = reinterpret_cast<int *>(team_smem + (size_t) kTeams * A.n_ind_pad);   // [kTeams][n_ind_pad]
   __shared__ double2 part[2][kTeams][W];
   __shared__ double gpart[kTeams][W];
-  for (unsigned i = threadIdx.x; i < kTeams * A.n_ind_pad; i += THREADS) team_smem[i] = 0.0;
+  for (unsigned i = threadIdx.x; i < kTeams * A.n_ind_pad; i += THREADS) { mant_acc[i] = 1.0; expo_acc[i] = 0; }
   __syncthreads();
-  double *my_acc = team_smem + (size_t) team * A.n_ind_pad;
+  double *my_mant = mant_acc + (size_t) team * A.n_ind_pad;
+  int *my_expo = expo_acc + (size_t) team * A.n_ind_pad;
+  unsigned my_passes = 0;
 
   for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x) {
     const uint64_t site = (uint64_t) tile * kTeams + team;
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
 
+    // all loads of the tile are issued before the first coefficient is formed (one memory latency
+    // per tile instead of K): the coefficient arrays double as staging for L0, L2, L1, F
     double a0[K], a2[K], hh[K], na[K], nv[K], dz[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      const size_t at = (size_t) (i < A.n_ind ? i : 0) * A.site_block + sl;
+      a0[k] = A.gl0[at]; hh[k] = A.gl1[at]; a2[k] = A.gl2[at];
+      na[k] = A.post ? A.post[at] : 0.0;
+    }
     double g_sum = 0.0;
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
-      IndCoef c;
-      if (i < A.n_ind) {
-        const size_t at = (size_t) i * A.site_block + sl;
-        const double F = A.post ? A.post[at] : 0.0;
-        c = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], F);
-      } else {
-        c = null_coef();
-      }
+      const IndCoef c = i < A.n_ind ? make_coef(a0[k], hh[k], a2[k], na[k]) : null_coef();
       a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; dz[k] = c.da - c.na;
       g_sum += c.g;
     }
@@ -411,12 +420,13 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
 #pragma unroll
       for (int w = 0; w < W; w++) g_sum += gpart[team][w];
 
-      double num = 0.0, dmn_next = g_sum, odds = kStartOdds;
+      double num = 0.0, dmn_next = g_sum, odds = kStartOdds, prev = kStartFreq;
       bool active = site_ok;                            // identical in every thread of the team
       int passes = 0;
+      double S[K];
+      pass_denominators<K>(a0, a2, hh, odds, S);
       while (active) {
-        double X, Z, S[K];
-        pass_denominators<K>(a0, a2, hh, odds, S);
+        double X, Z;
         pass_sums<K>(S, na, nv, dz, odds, X, Z);
 #pragma unroll
         for (int m = 1; m < 32; m <<= 1) {
@@ -433,12 +443,13 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         num = fma(odds, X, num);
         const double dmn = fma(odds, Z, dmn_next);
         odds = num * rcp_pos(dmn);
+        pass_denominators<K>(a0, a2, hh, odds, S);      // next pass, ahead of the stop test (see the warp kernel)
         dmn_next = dmn + g_sum;
-        const double before = freq;
         freq = num * rcp_pos<true>(num + dmn);
-        active = (fabs(before - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
+        active = (fabs(prev - freq) > kEps) && (passes <= 100);   // gen_func.cpp:1006
+        prev = freq;
       }
-      if (site_ok && grp == 0) { A.freq[site] = freq; atomicAdd(A.pass_total, (unsigned long long) passes); }
+      if (site_ok && grp == 0) { A.freq[site] = freq; my_passes += passes; }
       team_barrier(team, G);                            // gpart / part are reused by the next tile
     }
 
@@ -449,18 +460,22 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         const size_t at = (size_t) i * A.site_block + site;
         double e0, e1;
         emissions(a0[k], A.gl1[at], a2[k], freq, e0, e1);
-        *emis_slot(A, i, site) = e1 / e0;
+        *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
         if (A.e0) A.e0[at] = e0;
-        my_acc[i] += log(e0);                           // each (team, individual) slot has one writer
+        int e;                                          // each (team, individual) slot has one writer
+        my_mant[i] = split_exponent(my_mant[i] * e0, e);
+        my_expo[i] += e;
       }
     }
   }
+  if (my_passes) atomicAdd(A.pass_total, (unsigned long long) my_passes);
   __syncthreads();
   for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += THREADS) {
-    double s = 0.0;
+    double m = 1.0;
+    int e = 0;
 #pragma unroll
-    for (int t = 0; t < kTeams; t++) s += team_smem[(size_t) t * A.n_ind_pad + i];
-    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = s;
+    for (int t = 0; t < kTeams; t++) { m *= mant_acc[(size_t) t * A.n_ind_pad + i]; e += expo_acc[(size_t) t * A.n_ind_pad + i]; }
+    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = fma((double) e, 0.6931471805599453, log(m));
   }
 }
 
@@ -671,7 +686,7 @@ static void launch_team_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   constexpr int kThreads = W <= 4 ? 128 : 256;
   constexpr int kTeams = (kThreads / 32) / W;
   const unsigned tiles = (unsigned) ((a.sites_owned + kTeams - 1) / kTeams);
-  size_t smem = (size_t) kTeams * a.n_ind_pad * sizeof(double);
+  size_t smem = (size_t) kTeams * a.n_ind_pad * (sizeof(double) + sizeof(int));
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(freq_emission_team<W, K, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
