@@ -208,7 +208,10 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   const size_t plane_rec = (size_t) ctx->n_ranks * ctx->n_loc * ctx->site_block * sizeof(double);
   const size_t plane_frq = (size_t) ctx->n_ind_pad * ctx->site_block * sizeof(double);   // same number
   NFH_TRY(alloc((void **) &ctx->dist, ctx->n_sites_pad * sizeof(double), true));
-  NFH_TRY(alloc((void **) &ctx->emis_recv, plane_rec, true));
+  // emission-ratio windows start as 1.0 everywhere and the kernels only ever write real sites, so the
+  // padding of the last tile stays the identity of the recursions (r = 1 with d = 0)
+  NFH_TRY(alloc((void **) &ctx->emis_recv, plane_rec, false));
+  launch_fill(ctx->emis_recv, 1.0, plane_rec / sizeof(double), ctx->stream);
   NFH_TRY(alloc((void **) &ctx->post_send, plane_rec, true));
   NFH_TRY(alloc((void **) &ctx->indF, ctx->n_loc * sizeof(double), true));
   NFH_TRY(alloc((void **) &ctx->alpha, ctx->n_loc * sizeof(double), true));
@@ -227,7 +230,8 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
     ctx->emis_send = ctx->emis_recv;
   } else {
     NFH_TRY(alloc((void **) &ctx->post_recv, plane_frq, true));
-    NFH_TRY(alloc((void **) &ctx->emis_send, plane_frq, true));
+    NFH_TRY(alloc((void **) &ctx->emis_send, plane_frq, false));
+    launch_fill(ctx->emis_send, 1.0, plane_frq / sizeof(double), ctx->stream);
   }
   NFH_TRY(alloc((void **) &ctx->freq, ctx->site_block * sizeof(double), true));
   ctx->loge0_rows = (unsigned) ctx->sm_count * 4u;

@@ -84,26 +84,21 @@ __device__ __forceinline__ int renorm2(double &x, double &y) {
 // summed separately (the log_scale argument of site_kappa).
 //
 // Chromosome starts have d = +inf (c = 0, T_s = 1 q').  They, and any site with
-// alpha d > 76, use kappa = 2^110 and the scalar 2^-110.  The neglected term
-// I/kappa must vanish against kappa q_l for the smallest q_l the optimiser can
-// reach (1e-15 ~ 2^-50, EM.cpp:425-426): 2^-110 / 2^-50 = 2^-60, below half an
-// ulp.  Growth is bounded by renormalising at least every 6 sites (2^660).
+// alpha d > 110 ln 2, are evaluated at x = 110 ln 2 (kappa = 2^110 - 1, scalar 2^-110): one
+// clamp, no selects.  The neglected term I/kappa must vanish against kappa q_l for the
+// smallest q_l the optimiser can reach (1e-15 ~ 2^-50, EM.cpp:425-426): 2^-110 / 2^-50 = 2^-60,
+// below half an ulp.  Growth is bounded by renormalising at least every 6 sites (2^660).
 // ---------------------------------------------------------------------------
-constexpr double kBigX = 76.0;                        // e^76 < 2^110
-constexpr double kBigKappa = 1.2980742146337069e33;   // 2^110
-constexpr double kBigLogScale = 76.24618986159398;    // 110 ln 2
+constexpr double kBigX = 76.24618986159398;           // 110 ln 2: largest exponent of the factored form
 
-// kappa for x = alpha * d; adds log c (natural log) to log_scale.
+// kappa for x = alpha * d; adds log c = -x (natural log) to log_scale.
 __device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab, double &log_scale) {
-  const bool big = !(x <= kBigX);                     // also catches +inf and NaN
-  const double k = expm1_pos(big ? 0.0 : x, tab);
-  log_scale -= big ? kBigLogScale : x;
-  return big ? kBigKappa : k;
+  const double xc = fmin(x, kBigX);                   // fmin also maps NaN to the clamp
+  log_scale -= xc;
+  return expm1_pos(xc, tab);
 }
 __device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab) {
-  const bool big = !(x <= kBigX);
-  const double k = expm1_pos(big ? 0.0 : x, tab);
-  return big ? kBigKappa : k;
+  return expm1_pos(fmin(x, kBigX), tab);
 }
 
 // M <- M * N_s with k0 = kappa q0, k1 = kappa q1:

@@ -68,14 +68,13 @@ estep_chunk_products(const double *__restrict__ emis, const double *__restrict__
   const uint64_t tile_first = (uint64_t) tile * kTile;
   stage_tile(sm, emis + blocked_index(row, tile_first, n_rows, site_block), dist + tile_first);
 
-  const int n_valid = valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, n_sites);
   const double F = indF[row], al = alpha[row];
   const double q0 = 1.0 - F, q1 = F;
   const double *r = sm.r + threadIdx.x * kChunk;
   const double *d = sm.d + threadIdx.x * kChunk;
 
-  // Straight-line bodies of kBody sites (no branches inside: padding sites are turned into the
-  // identity by selecting r = 1; their distance is 0, so kappa = 0 and the scale term is 0).
+  // Straight-line bodies of kBody sites, no branches and no selects: padding sites are the identity
+  // because the context keeps r = 1 and d = 0 there (kappa = 0, scale term 0).
   M2 m = identity2();
   int e = 0;
   double ls = 0.0;
@@ -86,14 +85,14 @@ estep_chunk_products(const double *__restrict__ emis, const double *__restrict__
     for (int i = 0; i < kBody; i++) {
       const int j = j0 + i;
       const double kap = site_kappa(al * d[j], sm.tab, ls);
-      apply_site(m, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
+      apply_site(m, kap * q0, kap * q1, r[j]);
     }
     e += renorm(m);
   }
 #pragma unroll
   for (int j = (kChunk / kBody) * kBody; j < kChunk; j++) {
     const double kap = site_kappa(al * d[j], sm.tab, ls);
-    apply_site(m, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
+    apply_site(m, kap * q0, kap * q1, r[j]);
   }
   e += renorm(m);
   // per-chunk product (direction only: the apply kernel is scale free)
@@ -299,7 +298,7 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
       const int j = sb * kSub + i;
       const double kap = site_kappa(al * d[j], sm.tab);     // padding: d = 0 -> kappa = 0
       d[j] = kap;
-      forward_site(a0, a1, kap * q0, kap * q1, j < n_valid ? r[j] : 1.0);
+      forward_site(a0, a1, kap * q0, kap * q1, r[j]);
       if (i == kSub / 2) renorm2(a0, a1);
     }
   }
@@ -316,7 +315,7 @@ estep_chunk_apply(const double *__restrict__ emis, const double *__restrict__ di
 #pragma unroll
     for (int i = 0; i < kSub; i++) {
       const int j = sb * kSub + i;
-      rr[i] = j < n_valid ? r[j] : 1.0;
+      rr[i] = r[j];
       const double kap = d[j];
       k0[i] = kap * q0; k1[i] = kap * q1;
       forward_site(a0, a1, k0[i], k1[i], rr[i]);
@@ -394,7 +393,7 @@ __host__ __device__ constexpr int lkl_split(int NS, int NA) {
 // layout is fixed per group, so the whole body is straight-line code.  Lane 0 of every warp leaves
 // the warp's ordered product in shared memory.
 template <int NS, int NA>
-__device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklSmem &sm, int t, int n_valid) {
+__device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklSmem &sm, int t) {
   constexpr int NP = NS + NA;
   constexpr int kBody = 6;
   const double *r = sm.r + t * kChunk;
@@ -410,7 +409,7 @@ __device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklS
 
   auto site = [&](int j) {
     const double dj = d[j];
-    const double rj = j < n_valid ? r[j] : 1.0;      // padding: identity (d = 0 -> kappa = 0)
+    const double rj = r[j];                          // padding: r = 1, d = 0 -> identity
     if (NS > 0) {
       const double ks = site_kappa(g.alpha[first] * dj, sm.tab, ls[0]);
 #pragma unroll
@@ -445,13 +444,13 @@ __device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklS
 }
 
 template <int NS, int NA>
-__device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, int half, int t, int n_valid) {
+__device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, int half, int t) {
   constexpr int k = lkl_split(NS, NA);
   constexpr int NSa = k < NS ? k : NS, NAa = k - NSa, NSb = NS - NSa, NAb = NA - NAa;
   if (half == 0) {
-    lkl_chunk_run<NSa, NAa>(g, 0, sm, t, n_valid);
+    lkl_chunk_run<NSa, NAa>(g, 0, sm, t);
   } else {
-    if constexpr (NSb + NAb > 0) lkl_chunk_run<NSb, NAb>(g, k, sm, t, n_valid);
+    if constexpr (NSb + NAb > 0) lkl_chunk_run<NSb, NAb>(g, k, sm, t);
   }
 }
 
@@ -480,9 +479,8 @@ lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ di
   }
   mbar_wait(&sm.bar, 0);
   const int half = threadIdx.x / kScanThreads, t = threadIdx.x % kScanThreads;
-  const int n_valid = valid_sites(tile_first + (uint64_t) t * kChunk, n_sites);
 
-#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_halves<ns, na>(g, sm, half, t, n_valid); break;
+#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_halves<ns, na>(g, sm, half, t); break;
   switch (g.n_same * 8 + (g.npts - g.n_same)) {
     NFH_LKL(1, 0) NFH_LKL(1, 1) NFH_LKL(1, 2) NFH_LKL(1, 3) NFH_LKL(1, 4)
     NFH_LKL(2, 0) NFH_LKL(2, 1) NFH_LKL(2, 2) NFH_LKL(2, 3)

@@ -746,6 +746,14 @@ int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
   return 2;
 }
 
+__global__ void fill_double(double *__restrict__ dst, double value, size_t n) {
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) dst[i] = value;
+}
+
+void launch_fill(double *dst, double value, size_t n, cudaStream_t st) {
+  fill_double<<<1184, 256, 0, st>>>(dst, value, n);
+}
+
 void launch_reduce_loge0(const double *part, unsigned n_part, uint64_t n_ind_pad, double *out, cudaStream_t st) {
   reduce_loge0<<<(unsigned) ((n_ind_pad + 127) / 128), 128, 0, st>>>(part, n_part, n_ind_pad, out);
 }

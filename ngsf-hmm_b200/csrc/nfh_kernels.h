@@ -86,6 +86,7 @@ struct ViterbiArgs {
 void launch_estep(const EstepArgs &a, cudaStream_t st);
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st);
 // returns the grid size used (rows of loge0_part)
+void launch_fill(double *dst, double value, size_t n, cudaStream_t st);
 unsigned freq_grid_size(const FreqArgs &a, int sm_count);
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st);
 void launch_reduce_loge0(const double *part, unsigned n_part, uint64_t n_ind_pad, double *out, cudaStream_t st);
