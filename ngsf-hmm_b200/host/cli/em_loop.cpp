@@ -53,7 +53,7 @@ size_t first_max(const std::vector<double> &v) {
 
 }  // namespace
 
-void run_em(RunState &st) {
+void run_em(RunState &st, bool write_final) {
   Options &o = st.opt;
   const uint64_t N = o.n_ind, S = o.n_sites;
   g_keep_going = 1;
@@ -123,12 +123,12 @@ void run_em(RunState &st) {
   check(st, nfh_emission_refresh(st.ctx, 1), "nfh_emission_refresh");
   check(st, nfh_viterbi(st.ctx, st.path.data()), "nfh_viterbi");
 
-  if (o.verbose >= 1) {
-    printf("Final logLkl: %f\n", st.tot_lkl);
-    printf("Printing final results\n");
-  }
+  if (o.verbose >= 1) printf("Final logLkl: %f\n", st.tot_lkl);
   check(st, nfh_get_posterior(st.ctx, st.marg1.data()), "nfh_get_posterior");
-  write_outputs(st);
+  if (write_final) {
+    if (o.verbose >= 1) printf("Printing final results\n");
+    write_outputs(st);
+  }
 }
 
 }  // namespace nfh_cli

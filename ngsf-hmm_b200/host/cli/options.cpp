@@ -41,9 +41,10 @@ void parse_options(Options &o, int argc, char **argv) {
       {"min_iters", required_argument, nullptr, 'm'}, {"max_iters", required_argument, nullptr, 'M'},
       {"min_epsilon", required_argument, nullptr, 'E'}, {"n_threads", required_argument, nullptr, 'x'},
       {"verbose", required_argument, nullptr, 'V'},   {"seed", required_argument, nullptr, 'S'},
-      {"device", required_argument, nullptr, 'D'},    {nullptr, 0, nullptr, 0}};
+      {"device", required_argument, nullptr, 'D'},    {"n_rep", required_argument, nullptr, 'R'},
+      {nullptr, 0, nullptr, 0}};
   int c;
-  while ((c = getopt_long_only(argc, argv, "g:Z:lLn:s:Gf:F:e:i:IAo:X:b:m:M:E:x:V:S:D:", table, nullptr)) != -1) {
+  while ((c = getopt_long_only(argc, argv, "g:Z:lLn:s:Gf:F:e:i:IAo:X:b:m:M:E:x:V:S:D:R:", table, nullptr)) != -1) {
     switch (c) {
       case 'g': o.geno = optarg; o.have_geno = true; break;
       case 'Z': o.pos = optarg; o.have_pos = true; break;
@@ -68,6 +69,7 @@ void parse_options(Options &o, int argc, char **argv) {
       case 'V': o.verbose = (unsigned) atoi(optarg); break;
       case 'S': o.seed = (unsigned) atoi(optarg); break;
       case 'D': o.device = atoi(optarg); break;
+      case 'R': o.n_rep = (unsigned) atoi(optarg); break;
       default: exit(-1);
     }
   }
@@ -102,6 +104,7 @@ void parse_options(Options &o, int argc, char **argv) {
   if (!o.have_out) fatal(fn, "output prefix (--out) missing!");
   if (o.min_iters < 1 || o.max_iters < 1 || o.min_iters >= o.max_iters) fatal(fn, "invalid number of iterations!");
   if (o.n_threads < 1) fatal(fn, "invalid number of threads!");
+  if (o.n_rep < 1) fatal(fn, "invalid number of replicates!");
   // The haplotype-frequency paths abort in the reference itself (freq[0] = -1 reaches haplo_freq,
   // gen_func.cpp:1030-1031); keep the same message instead of inventing behaviour.
   if (o.freq_est == 2 || o.e_prob == 2) fatal("haplo_freq", "invalid allele frequencies");

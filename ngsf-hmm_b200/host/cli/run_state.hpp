@@ -23,6 +23,9 @@ struct Options {   // one field per command-line flag of the reference (parse_ar
   double min_epsilon = 1e-5;
   bool have_geno = false, have_pos = false, have_out = false;
   int device = 0;          // --device (extension; not a reference flag)
+  unsigned n_rep = 1;      // --n_rep (extension): replicates of the whole EM from different --seed values on one
+                           // ingest and one GL upload; the best final logLkl is written (what ngsF-HMM.sh does
+                           // with one process, one parse and one upload per replicate)
 };
 
 struct RunState {
@@ -47,9 +50,10 @@ void parse_options(Options &o, int argc, char **argv);
 void read_positions(RunState &st);
 void read_genotypes(RunState &st);
 // startvalues.cpp
-void init_start_values(RunState &st);
+void create_device_state(RunState &st);                   // context + GL / distance upload (once per process)
+void init_start_values(RunState &st, unsigned seed);      // start values + initial emissions (once per replicate)
 // em_loop.cpp
-void run_em(RunState &st);
+void run_em(RunState &st, bool write_final);              // EM loop, Viterbi, posterior; outputs if write_final
 // report.cpp
 void write_outputs(RunState &st);
 

@@ -76,11 +76,18 @@ void check(RunState &st, int rc, const char *where) {
   }
 }
 
-void init_start_values(RunState &st) {
+void create_device_state(RunState &st) {
+  Options &o = st.opt;
+  check(st, nfh_ctx_create(&st.ctx, o.device, o.n_ind, o.n_sites, 1, 0), "nfh_ctx_create");
+  check(st, nfh_upload_pos_dist(st.ctx, st.dist_mb.data()), "nfh_upload_pos_dist");
+  check(st, nfh_upload_gl(st.ctx, st.log_gl.data(), 0, o.n_sites), "nfh_upload_gl");
+}
+
+void init_start_values(RunState &st, unsigned seed) {
   Options &o = st.opt;
   const char *fn = "init_output";
   const uint64_t N = o.n_ind, S = o.n_sites;
-  Taus rng(o.seed);
+  Taus rng(seed);
   const double lo = 0.000001, hi = 1 - lo;
   st.indF.assign(N, 0.0);
   st.alpha.assign(N, 0.0);
@@ -144,10 +151,6 @@ void init_start_values(RunState &st) {
     for (uint64_t s = 0; s < S; s++) st.freq[s] = v;
   }
 
-  // device state
-  check(st, nfh_ctx_create(&st.ctx, o.device, N, S, 1, 0), "nfh_ctx_create");
-  check(st, nfh_upload_pos_dist(st.ctx, st.dist_mb.data()), "nfh_upload_pos_dist");
-  check(st, nfh_upload_gl(st.ctx, st.log_gl.data(), 0, S), "nfh_upload_gl");
   if (o.verbose >= 1) printf("==> Calculating initial emission probabilities\n");
   if (estimate) {
     check(st, nfh_freq_update(st.ctx, 1, 1, st.freq.data()), "nfh_freq_update");   // est_maf with F = 0
@@ -158,6 +161,8 @@ void init_start_values(RunState &st) {
   st.ind_lkl.assign(N, -INFINITY);
   st.path.assign(N * S, 0);
   st.marg1.assign(N * S, 0.0);
+  st.prev_tot_lkl = 0.0;
+  st.tot_lkl = 0.0;
 }
 
 }  // namespace nfh_cli

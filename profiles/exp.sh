@@ -1,2 +1,1 @@
-timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 600 python bench.py --steps 6 --warmup 3 --no_cpu_baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['ms_per_step'], d['kernel_ms_per_step'], d['final_loglkl_rank0'], d['e2e']['ms_per_step'], d['clocks'])"
+timeout 1200 python -m pytest tests/test_gpu_cli.py -x -q -m gpu 2>&1 | tail -15
