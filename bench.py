@@ -266,7 +266,7 @@ def main():
 
     F, a = reset_state()
     for _ in range(args.warmup):
-        runner.iteration(F, a, want_freq=False)
+        runner.iteration(F, a, want_freq=True)       # also page-locks the frequency download buffer (one-off)
 
     # ---- device-timed region: K successive EM iterations, state resident in HBM
     ctx.timing(True)

@@ -156,6 +156,12 @@ int nfh_peer_export(nfh_ctx *ctx, int window, unsigned char handle[64]);
 int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char handle[64]);
 int nfh_peer_direct(nfh_ctx *ctx, int enable);
 
+/* Page-lock a caller-owned host array (cudaHostRegister) so that the copies of the calls above move at
+ * full PCIe speed instead of being staged: worth it for the arrays that cross every EM iteration
+ * (freq_out of nfh_freq_update is 8 bytes per site).  Unregister before freeing the array. */
+int nfh_host_register(nfh_ctx *ctx, void *ptr, uint64_t bytes);
+int nfh_host_unregister(nfh_ctx *ctx, void *ptr);
+
 /* Block until everything queued by this context has finished; returns the
  * sticky device status (NaN / FwBw flags raised by kernels). */
 int nfh_sync(nfh_ctx *ctx);

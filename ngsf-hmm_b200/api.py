@@ -28,7 +28,7 @@ EXPORTS = [
     "nfh_upload_gl", "nfh_upload_pos_dist", "nfh_set_freq", "nfh_get_freq", "nfh_set_ind_params",
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
-    "nfh_timing_read", "nfh_freq_passes",
+    "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister",
 ]
 
 
@@ -98,6 +98,8 @@ def load_library():
     L.nfh_timing.restype = cint; L.nfh_timing.argtypes = [_vp, cint]
     L.nfh_timing_read.restype = cint; L.nfh_timing_read.argtypes = [_vp, _dp, C.POINTER(u64), cint]
     L.nfh_freq_passes.restype = cint; L.nfh_freq_passes.argtypes = [_vp, C.POINTER(u64), cint]
+    L.nfh_host_register.restype = cint; L.nfh_host_register.argtypes = [_vp, _vp, u64]
+    L.nfh_host_unregister.restype = cint; L.nfh_host_unregister.argtypes = [_vp, _vp]
     _lib = L
     return L
 
@@ -123,6 +125,7 @@ class Context:
         if rc != 0:
             raise NfhError(rc, self.L.nfh_last_error(None).decode())
         self.h = h
+        self._pinned = []
         self.n_ind_total, self.n_sites, self.n_ranks, self.rank = n_ind_total, n_sites, n_ranks, rank
         self.n_ind_local = self.L.nfh_n_ind_local(h)
         self.n_ind_owned = self.L.nfh_n_ind_owned(h)
@@ -138,6 +141,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for a in getattr(self, "_pinned", []):
+                self.L.nfh_host_unregister(self.h, a.ctypes.data)
+            self._pinned = []
             self.L.nfh_ctx_destroy(self.h)
             self.h = None
 
@@ -205,8 +211,15 @@ class Context:
                                        _p(out)))
         return out
 
-    def freq_update(self, method=1, posterior_is_zero=False, want_freq=True):
-        f = np.empty(self.sites_owned) if want_freq else None
+    def pinned_empty(self, n):
+        """float64 host array of n elements, page-locked until the context is closed (full-speed copies)."""
+        a = np.empty(max(int(n), 1))
+        self._chk(self.L.nfh_host_register(self.h, a.ctypes.data, a.nbytes))
+        self._pinned.append(a)
+        return a[:int(n)]
+
+    def freq_update(self, method=1, posterior_is_zero=False, want_freq=True, out=None):
+        f = (out if out is not None else np.empty(self.sites_owned)) if want_freq else None
         self._chk(self.L.nfh_freq_update(self.h, method, int(posterior_is_zero), _p(f) if want_freq else None))
         return f
 

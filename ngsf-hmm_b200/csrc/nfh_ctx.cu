@@ -662,6 +662,18 @@ int nfh_timing_read(nfh_ctx *ctx, double ms_out[8], uint64_t launches_out[8], in
   return NFH_OK;
 }
 
+int nfh_host_register(nfh_ctx *ctx, void *ptr, uint64_t bytes) {
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  NFH_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  return NFH_OK;
+}
+
+int nfh_host_unregister(nfh_ctx *ctx, void *ptr) {
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  NFH_CUDA(cudaHostUnregister(ptr));
+  return NFH_OK;
+}
+
 int nfh_freq_passes(nfh_ctx *ctx, uint64_t *total, int reset) {
   NFH_CUDA(cudaSetDevice(ctx->device));
   unsigned long long v = 0;

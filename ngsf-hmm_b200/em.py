@@ -70,6 +70,7 @@ class EmRank:
         self.stats = np.zeros(3, dtype=np.uint64)
         self.total_evals = 0
         self.total_rounds = 0
+        self._freq_host = None        # page-locked home of the per-iteration frequency download
         self._win = {}
         self._ext_stream = None
         self._side = None
@@ -185,11 +186,14 @@ class EmRank:
 
     def iteration(self, indF, alpha, want_freq=True):
         """One EM iteration; indF/alpha (float64, n_ind_owned) are updated in place.
-        Returns (ind_lkl, freq_of_this_rank's_sites or None)."""
+        Returns (ind_lkl, freq_of_this_rank's_sites or None); the frequency array is one page-locked
+        buffer that every call overwrites (copy it to keep an iteration's values)."""
         ctx = self.ctx
+        if want_freq and self.freq_est and self._freq_host is None:
+            self._freq_host = ctx.pinned_empty(ctx.sites_owned)    # crosses PCIe every iteration: page-locked
         if ctx.n_ranks == 1:
             lk = np.empty(ctx.n_ind_owned)
-            fr = np.empty(ctx.sites_owned) if (want_freq and self.freq_est) else None
+            fr = self._freq_host if (want_freq and self.freq_est) else None
             rc = self.H.nfh_host_em_iteration(ctx.h, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
                                               int(self.indF_fixed), int(self.alpha_fixed), int(self.freq_est),
                                               lk.ctypes.data_as(_dp), fr.ctypes.data_as(_dp) if fr is not None else None,
@@ -206,11 +210,11 @@ class EmRank:
         if self.freq_est:
             if self.direct:
                 self._rank_fence()                       # every rank's E-step stores have landed
-                fr = ctx.freq_update(1, want_freq=want_freq)
+                fr = ctx.freq_update(1, want_freq=want_freq, out=self._freq_host)
                 self._allreduce_loge0()                  # + fence: every rank's emission stores have landed
             else:
                 self.exchange_posteriors_end()
-                fr = ctx.freq_update(1, want_freq=want_freq)
+                fr = ctx.freq_update(1, want_freq=want_freq, out=self._freq_host)
                 self.exchange_emissions()
         return lk, fr
 

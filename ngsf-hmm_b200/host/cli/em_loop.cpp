@@ -59,6 +59,9 @@ void run_em(RunState &st, bool write_final) {
   g_keep_going = 1;
   install_handlers();
 
+  // the frequencies come back every iteration (8 bytes per site): page-lock their host array
+  const bool pinned = nfh_host_register(st.ctx, st.freq.data(), S * sizeof(double)) == NFH_OK;
+
   uint64_t iter = 0;
   double max_eps = -INFINITY;
   std::vector<double> prev_lkl(N, -INFINITY), eps(N, -INFINITY);
@@ -117,6 +120,8 @@ void run_em(RunState &st, bool write_final) {
     fflush(stdout);
   }
   if (iter >= o.max_iters) printf("WARN: Maximum number of iterations reached! Check if analysis converged... \n");
+
+  if (pinned) nfh_host_unregister(st.ctx, st.freq.data());
 
   if (o.verbose >= 1) printf("\n==> Decoding most probable path (Viterbi)\n");
   check(st, nfh_set_ind_params(st.ctx, st.indF.data(), st.alpha.data()), "nfh_set_ind_params");
