@@ -148,6 +148,9 @@ __device__ __forceinline__ void pass_sums(const double (&S)[K], const double (&n
 // est_maf starts every site at f = 0.01 (gen_func.cpp:980)
 constexpr double kStartFreq = 0.01;
 constexpr double kStartOdds = 0.01 / 0.99;
+// A site fixed for the minor allele drives den - num to 0 (or to a rounding residue of either sign):
+// the odds are capped at 1e35, i.e. f = 1 to the last bit, and S/u ~ 1e70 keeps four-way products finite.
+constexpr double kMinOddsInv = 1e-35;
 
 // Resident CTAs per SM the register budget of K individuals per lane allows
 // (12 K registers of coefficients + 4 K of per-pass temporaries + ~40).
@@ -298,7 +301,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
           Z += __shfl_xor_sync(kFull, Z, m);
         }
         num = fma(odds, X, num);
-        const double dmn = fma(odds, Z, dmn_next);
+        const double dmn = fmax(fma(odds, Z, dmn_next), num * kMinOddsInv);   // f -> 1: odds stay finite
         odds = num * rcp_pos(dmn);
         // the next pass starts here, inside the same basic block, so that the compiler schedules the
         // chain num -> odds -> S ahead of the stop test (one wasted set of denominators at the exit)
@@ -441,7 +444,7 @@ freq_emission_team(FreqArgs A, unsigned n_site_tiles) {
         for (int w = 0; w < W; w++) { const double2 q = part[buf][team][w]; X += q.x; Z += q.y; }
         passes++;
         num = fma(odds, X, num);
-        const double dmn = fma(odds, Z, dmn_next);
+        const double dmn = fmax(fma(odds, Z, dmn_next), num * kMinOddsInv);   // f -> 1: odds stay finite
         odds = num * rcp_pos(dmn);
         pass_denominators<K>(a0, a2, hh, odds, S);      // next pass, ahead of the stop test (see the warp kernel)
         dmn_next = dmn + g_sum;

@@ -1,1 +1,1 @@
-timeout 600 python bench.py --steps 8 --warmup 3 --no_cpu_baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['ms_per_step'], d['kernel_ms_per_step'], d['e2e'])"
+timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -5

@@ -141,6 +141,31 @@ def test_freq_update_large_n_variants(oracle, N, S):
         np.testing.assert_allclose(lk2, lk2_o, rtol=LKL_RTOL)
 
 
+def test_freq_update_hard_calls_and_monomorphic_sites(oracle):
+    """Called genotypes (GL exactly 0/1) with sites fixed for either allele or all heterozygous: the
+    frequency reaches exactly 0 or 1 (allele odds 0 / unbounded) and posteriors are clamped to 0 or 1."""
+    rng = np.random.default_rng(5)
+    N, S = 12, 96
+    d, ctx = _setup(N, S, 41, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    geno = rng.integers(0, 3, size=(N, S))
+    geno[:, 0] = 0; geno[:, 1] = 2; geno[:, 2] = 1; geno[:, 3] = 2; geno[:6, 4] = 0; geno[6:, 4] = 2
+    geno[:, 40:48] = 2; geno[:, 60:64] = 0
+    gl = np.full((N, S, 3), -np.inf)
+    np.put_along_axis(gl, geno[:, :, None], 0.0, axis=2)
+    d.log_gl = np.ascontiguousarray(np.transpose(gl, (1, 0, 2)))
+    with ctx:
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.2, 0.3, 0.5)
+        for _ in range(2):
+            ctx.estep()
+            post = ctx.get_posterior()
+            f_new = ctx.freq_update(1)
+            f_o, e_o = oracle.freq_emission(gl_ind, post, freq, update_freq=True)
+            assert np.isfinite(f_new).all()
+            np.testing.assert_allclose(f_new, f_o, rtol=0, atol=1e-11)
+            assert f_new[0] == 0.0 and abs(f_new[1] - 1.0) < 1e-15 and abs(f_new[2] - 0.5) < 1e-15
+            freq = f_o
+
+
 def test_freq_pass_counter_matches_oracle(oracle):
     """nfh_freq_passes (the work figure behind bench.py's roofline) = the oracle's est_maf pass counts."""
     d, ctx = _setup(20, 500, 77, freq=(0.02, 0.5), indF=(0.0, 0.5))
