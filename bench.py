@@ -146,7 +146,7 @@ class ClockSampler:
 
 def ncu_traffic():
     """DRAM bytes per individual-site measured by ncu (committed under profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01c.json")
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01f.json")
     try:
         with open(path) as fh:
             return json.load(fh)["bytes_per_ind_site"]
