@@ -376,6 +376,7 @@ static int run_freq_family(nfh_ctx *ctx, int family, int update, bool zero_post,
   a.n_ind = ctx->n_ind_total; a.n_ind_pad = ctx->n_ind_pad;
   a.site_block = ctx->site_block; a.sites_owned = ctx->sites_owned;
   a.update_freq = update;
+  freq_tensor_maps(a, ctx->post_recv);
   if (ctx->sites_owned == 0) {
     NFH_CUDA(cudaMemsetAsync(ctx->loge0_sum, 0, ctx->n_ind_pad * sizeof(double), ctx->stream));
     return NFH_OK;

@@ -173,17 +173,32 @@ __device__ __forceinline__ void emissions(double L0, double L1, double L2, doubl
   e1 = fma(L0, u + a, L2 * (v + a));       // het prior is exp(-1e15) = 0 when F == 1
 }
 
-// Shared-memory layout of one site tile of freq_emission_warp: row r = plane * n_ind + i holds the
-// CTA's sites of individual i (planes: GL0, GL1, GL2, posterior).  Rows are skewed by 16 bytes (the
-// TMA alignment) every 2^skew rows so that the lanes of a half-warp (different individuals, 1-4
-// neighbouring sites) spread over the banks: skew 0 is conflict-free, 1 two-way, ... 31 no padding.
+// Shared-memory image of one site tile of freq_emission_warp.  Each of the four planes (GL0, GL1, GL2,
+// posterior; [n_ind_pad][site_block] in HBM) is fetched as 2-D tensor boxes of (<= 256 individuals) x
+// (<= 16 sites) by cp.async.bulk.tensor - a handful of copies per tile issued by one thread, instead of
+// one bulk copy per individual row (ncu r01f: issuing 400 row copies per tile cost 8 % of the kernel).
+// The boxes are swizzled (32/64/128-byte pattern = the row length) so that the lanes of a half-warp,
+// which read different individuals at 1-4 neighbouring sites, spread over the banks.
 template <int G> struct FreqTile {
   static constexpr int kSitesPerWarp = 32 / G;
   static constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
-  static constexpr int kPad = G == 4 ? 4 : 2;                          // doubles
-  static constexpr uint32_t kRowBytes = kSitesPerCta * sizeof(double);
-  __host__ __device__ static size_t row_offset(size_t r, int skew) { return r * kSitesPerCta + kPad * (r >> skew); }
-  __host__ __device__ static size_t tile_doubles(uint64_t n_ind, int skew) { return row_offset(4 * n_ind, skew) + kPad; }
+  static constexpr int kInner = kSitesPerCta < 16 ? kSitesPerCta : 16;   // sites per box row
+  static constexpr int kInnerBytes = kInner * 8;                         // 32, 64 or 128 = swizzle span
+  static constexpr int kBoxesX = kSitesPerCta / kInner;
+  static constexpr int kMaxBoxRows = 256;
+  static constexpr unsigned kSwizzleMask = kInnerBytes / 16 - 1;
+  static constexpr unsigned kAlign = 8 * kInnerBytes;                    // period of the swizzle pattern in bytes
+  __host__ __device__ static unsigned box_rows(uint64_t n_ind) { return n_ind < kMaxBoxRows ? (unsigned) n_ind : kMaxBoxRows; }
+  __host__ __device__ static unsigned boxes_y(uint64_t n_ind) { return (unsigned) ((n_ind + kMaxBoxRows - 1) / kMaxBoxRows); }
+  __host__ __device__ static size_t region_bytes(uint64_t n_ind) { return ((size_t) box_rows(n_ind) * kInnerBytes + kAlign - 1) / kAlign * kAlign; }
+  __host__ __device__ static size_t tile_bytes(uint64_t n_ind) { return 4 * kBoxesX * boxes_y(n_ind) * region_bytes(n_ind); }
+  // byte offset of (plane, individual i, site s of the CTA tile) inside a tile buffer (kAlign-aligned)
+  __device__ static size_t offset(unsigned plane, unsigned i, unsigned s, uint64_t n_ind) {
+    const unsigned region = (plane * kBoxesX + s / kInner) * boxes_y(n_ind) + i / kMaxBoxRows;
+    unsigned off = (i % kMaxBoxRows) * kInnerBytes + (s % kInner) * 8;
+    off ^= ((off >> 7) & kSwizzleMask) << 4;
+    return region * region_bytes(n_ind) + off;
+  }
   // per warp and individual: running product of e0 (mantissa in [1,2) as double + exponent as int)
   __host__ __device__ static size_t acc_doubles(uint64_t n_ind_pad) { return (((size_t) (kFreqThreads / 32) * n_ind_pad * 3 / 2 + 15) / 16) * 16; }
 };
@@ -202,7 +217,7 @@ template <int G> struct FreqTile {
 // reciprocal after the reduction, and the stop test + vote hang off the side of the chain.
 template <int G, int K, bool PREFETCH, int OCC = freq_occupancy(K)>
 __global__ void __launch_bounds__(kFreqThreads, OCC)
-freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
+freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
   using Tile = FreqTile<G>;
   constexpr int kSitesPerWarp = Tile::kSitesPerWarp;
   constexpr int kSitesPerCta = Tile::kSitesPerCta;
@@ -216,28 +231,28 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
   double *my_mant = mant_acc + (size_t) warp * A.n_ind_pad;
   int *my_expo = expo_acc + (size_t) warp * A.n_ind_pad;
 
-  // ---- prefetch machinery
+  // ---- prefetch machinery: two tile buffers (aligned to the swizzle period), one mbarrier each
   const unsigned n_planes = A.post ? 4u : 3u;
-  const unsigned n_rows = n_planes * (unsigned) A.n_ind;
-  const size_t buf_doubles = Tile::tile_doubles(A.n_ind, skew);
-  double *bufs = freq_smem + Tile::acc_doubles(A.n_ind_pad);
+  const size_t buf_bytes = Tile::tile_bytes(A.n_ind);
+  unsigned char *bufs = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(freq_smem + Tile::acc_doubles(A.n_ind_pad)) + Tile::kAlign - 1) & ~(uintptr_t) (Tile::kAlign - 1));
   __shared__ alignas(8) uint64_t bars[2];
-  auto issue_tile = [&](unsigned t, int b) {
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(&bars[b], n_rows * Tile::kRowBytes);
-    __syncthreads();
-    const uint64_t first_site = (uint64_t) t * kSitesPerCta;
-    for (unsigned r = threadIdx.x; r < n_rows; r += kFreqThreads) {
-      const unsigned plane = r / (unsigned) A.n_ind, i = r - plane * (unsigned) A.n_ind;
-      const double *src = (plane == 0 ? A.gl0 : plane == 1 ? A.gl1 : plane == 2 ? A.gl2 : A.post) +
-                          (size_t) i * A.site_block + first_site;
-      tma_load_1d(bufs + (size_t) b * buf_doubles + Tile::row_offset(r, skew), src, Tile::kRowBytes, &bars[b]);
-    }
+  auto issue_tile = [&](unsigned t, int b) {      // thread 0 only
+    const unsigned by = Tile::boxes_y(A.n_ind);
+    const uint32_t box_bytes = Tile::box_rows(A.n_ind) * Tile::kInnerBytes;
+    mbar_arrive_expect_tx(&bars[b], n_planes * Tile::kBoxesX * by * box_bytes);
+    const int first_site = (int) (t * kSitesPerCta);
+    for (unsigned p = 0; p < n_planes; p++)
+      for (unsigned bx = 0; bx < (unsigned) Tile::kBoxesX; bx++)
+        for (unsigned y = 0; y < by; y++)
+          tma_load_2d(bufs + (size_t) b * buf_bytes + ((p * Tile::kBoxesX + bx) * by + y) * Tile::region_bytes(A.n_ind),
+                      &A.maps[p], first_site + (int) bx * Tile::kInner, (int) (y * Tile::kMaxBoxRows), &bars[b]);
   };
   if (PREFETCH) {
     if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   }
   __syncthreads();
-  if (PREFETCH && blockIdx.x < n_site_tiles) issue_tile(blockIdx.x, 0);
+  if (PREFETCH && threadIdx.x == 0 && blockIdx.x < n_site_tiles) issue_tile(blockIdx.x, 0);
 
   unsigned round = 0;
   unsigned my_passes = 0;                       // passes of the sites this lane reports (grp == 0)
@@ -246,9 +261,13 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
     const uint64_t site = (uint64_t) tile * kSitesPerCta + site_in_cta;
     const bool site_ok = site < A.sites_owned;
     const uint64_t sl = site_ok ? site : 0;
-    const double *tile_buf = bufs + (size_t) (round & 1) * buf_doubles;
+    const unsigned char *tile_buf = bufs + (size_t) (round & 1) * buf_bytes;
+    auto staged = [&](unsigned plane, uint64_t i) {
+      return *reinterpret_cast<const double *>(tile_buf + Tile::offset(plane, (unsigned) i, (unsigned) site_in_cta, A.n_ind));
+    };
     if (PREFETCH) {
-      if (tile + gridDim.x < n_site_tiles) issue_tile(tile + gridDim.x, (round & 1) ^ 1);
+      // the other buffer was last read before the __syncthreads that ended the previous tile
+      if (threadIdx.x == 0 && tile + gridDim.x < n_site_tiles) issue_tile(tile + gridDim.x, (round & 1) ^ 1);
       mbar_wait(&bars[round & 1], (round >> 1) & 1);
     }
 
@@ -260,11 +279,8 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
       const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
       const uint64_t il = i < A.n_ind ? i : 0;
       if (PREFETCH) {
-        const double *at = tile_buf + site_in_cta;
-        a0[k] = at[Tile::row_offset(il, skew)];
-        hh[k] = at[Tile::row_offset(A.n_ind + il, skew)];
-        a2[k] = at[Tile::row_offset(2 * A.n_ind + il, skew)];
-        na[k] = A.post ? at[Tile::row_offset(3 * A.n_ind + il, skew)] : 0.0;
+        a0[k] = staged(0, il); hh[k] = staged(1, il); a2[k] = staged(2, il);
+        na[k] = A.post ? staged(3, il) : 0.0;
       } else {
         const size_t at = (size_t) il * A.site_block + sl;
         a0[k] = A.gl0[at]; hh[k] = A.gl1[at]; a2[k] = A.gl2[at];
@@ -325,7 +341,7 @@ freq_emission_warp(FreqArgs A, unsigned n_site_tiles, int skew) {
       double pe0 = 1.0;
       if (i < A.n_ind && site_ok) {
         const size_t at = (size_t) i * A.site_block + site;
-        const double L1 = PREFETCH ? tile_buf[Tile::row_offset(A.n_ind + i, skew) + site_in_cta] : A.gl1[at];
+        const double L1 = PREFETCH ? staged(1, i) : A.gl1[at];
         double e0, e1;
         emissions(a0[k], L1, a2[k], freq, e0, e1);
         *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
@@ -664,24 +680,67 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   const unsigned per_cta = FreqTile<G>::kSitesPerCta;
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t acc = FreqTile<G>::acc_doubles(a.n_ind_pad) * sizeof(double);
-  // all resident CTAs of an SM must fit their double buffers in its 228 KB of shared memory (1 KB reserved each);
-  // take the least conflicting row skew that fits
+  // all resident CTAs of an SM must fit their double buffers in its 228 KB of shared memory (1 KB reserved each)
   const size_t smem_cap = (size_t) 228 * 1024 / freq_occupancy(K) - 1024 - 256;
-  int skew = 0;
-  size_t bufs = 0;
-  bool prefetch = false;
-  for (int sk : {0, 1, 2, 31}) {
-    bufs = 2 * FreqTile<G>::tile_doubles(a.n_ind, sk) * sizeof(double);
-    if (acc + bufs <= smem_cap) { skew = sk; prefetch = true; break; }
-  }
-  if (getenv("NFH_FREQ_NO_PREFETCH")) prefetch = false;
+  const size_t bufs = 2 * FreqTile<G>::tile_bytes(a.n_ind) + FreqTile<G>::kAlign;   // + alignment slack
+  const bool prefetch = a.use_maps && acc + bufs <= smem_cap && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
     attr_done = true;
   }
-  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles, skew);
-  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles, 31);
+  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
+  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles);
+}
+
+// Tensor maps of the four planes for the lane-group shape n_ind selects: [n_ind_pad][site_block] FP64,
+// box = (<= 256 rows) x (<= 16 sites), swizzle = box row length.  cuTensorMapEncodeTiled is taken from
+// the driver at run time so that the library does not link libcuda.
+template <int G>
+static bool encode_maps(FreqArgs &a, const double *post_plane, void *encode) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  using Tile = FreqTile<G>;
+  const double *planes[4] = {a.gl0, a.gl1, a.gl2, post_plane};
+  const cuuint64_t dims[2] = {a.site_block, a.n_ind_pad};
+  const cuuint64_t strides[1] = {a.site_block * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t) Tile::kInner, Tile::box_rows(a.n_ind)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle swz = Tile::kInnerBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : Tile::kInnerBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  for (int p = 0; p < 4; p++) {
+    if (!planes[p]) return false;
+    if (((EncodeFn) encode)(&a.maps[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *) planes[p], dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
+bool freq_tensor_maps(FreqArgs &a, const double *post_plane) {
+  a.use_maps = 0;
+  static void *encode = nullptr;
+  static bool looked = false;
+  if (!looked) {
+    looked = true;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      encode = nullptr;
+  }
+  int G, K;
+  if (!encode || !pick_shape(a.n_ind, G, K)) return false;
+  bool ok = false;
+  switch (G) {
+    case 4: ok = encode_maps<4>(a, post_plane, encode); break;
+    case 8: ok = encode_maps<8>(a, post_plane, encode); break;
+    case 16: ok = encode_maps<16>(a, post_plane, encode); break;
+    case 32: ok = encode_maps<32>(a, post_plane, encode); break;
+  }
+  a.use_maps = ok ? 1 : 0;
+  return ok;
 }
 
 template <int W, int K>

@@ -1,6 +1,6 @@
-// nfh_tma.cuh - 1-D bulk async copies (TMA, cp.async.bulk) with mbarrier
-// completion, for staging contiguous site tiles in shared memory.
-// SASS: UBLKCP (bulk copy) + SYNCS (mbarrier).
+// nfh_tma.cuh - bulk async copies (TMA) with mbarrier completion: 1-D (cp.async.bulk) for contiguous
+// site tiles, 2-D tensor copies (cp.async.bulk.tensor) for boxes of rows.
+// SASS: UBLKCP / UTMALDG (copies) + SYNCS (mbarrier).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -40,6 +40,15 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_addr(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// 2-D tiled tensor copy global -> shared through a CUtensorMap (box of rows x columns, optional swizzle);
+// coordinates are element indices, innermost first.  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_map, int x, int y, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_addr(smem_dst)),
+               "l"(tensor_map), "r"(x), "r"(y), "r"(smem_addr(bar))
                : "memory");
 }
 
