@@ -53,6 +53,7 @@ struct nfh_ctx {
   double *post_recv = nullptr, *emis_send = nullptr, *e0_send = nullptr, *freq = nullptr;
   double *loge0_part = nullptr, *loge0_sum = nullptr;
   unsigned long long *freq_passes = nullptr;   // device counter, see FreqArgs::pass_total
+  double *freq_acc = nullptr;                  // FreqArgs::acc_scratch (large n_ind only)
   unsigned loge0_rows = 0;
 
   // peer windows (CUDA IPC), see nfh_peer_*
@@ -239,6 +240,8 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   NFH_TRY(alloc((void **) &ctx->loge0_sum, ctx->n_ind_pad * sizeof(double), true));
   NFH_TRY(alloc((void **) &ctx->status, sizeof(int), true));
   NFH_TRY(alloc((void **) &ctx->freq_passes, sizeof(unsigned long long), true));
+  if (const size_t acc_bytes = freq_acc_scratch_bytes(ctx->n_ind_total, ctx->n_ind_pad, ctx->sm_count))
+    NFH_TRY(alloc((void **) &ctx->freq_acc, acc_bytes, false));
   NFH_TRY(alloc(&ctx->d_stage, kStageBytes, false));
   auto pinned = [&]() -> int {
     ctx->h_small_doubles = 8 * std::max<uint64_t>(ctx->n_loc * kMaxPoints, 64);
@@ -262,7 +265,7 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   void *dev[] = {ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
                  ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
                  ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
-                 ctx->status, ctx->freq_passes, ctx->d_stage};
+                 ctx->status, ctx->freq_passes, ctx->freq_acc, ctx->d_stage};
   for (void *p : dev) if (p) cudaFree(p);
   for (int r = 0; r < kMaxRanks; r++) {
     if (r == ctx->rank) continue;
@@ -370,6 +373,7 @@ static int run_freq_family(nfh_ctx *ctx, int family, int update, bool zero_post,
   a.freq = ctx->freq; a.emis = ctx->emis_send; a.e0 = with_e0 ? ctx->e0_send : nullptr;
   a.loge0_part = ctx->loge0_part;
   a.pass_total = ctx->freq_passes;
+  a.acc_scratch = ctx->freq_acc;
   a.emis_peers.direct = ctx->peer_direct ? 1 : 0;
   a.emis_peers.rank = ctx->rank; a.emis_peers.n_loc = ctx->n_loc;
   for (int r = 0; r < kMaxRanks; r++) a.emis_peers.base[r] = ctx->peer_emis[r];

@@ -188,16 +188,17 @@ template <int G> struct FreqTile {
   static constexpr int kMaxBoxRows = 256;
   static constexpr unsigned kSwizzleMask = kInnerBytes / 16 - 1;
   static constexpr unsigned kAlign = 8 * kInnerBytes;                    // period of the swizzle pattern in bytes
-  __host__ __device__ static unsigned box_rows(uint64_t n_ind) { return n_ind < kMaxBoxRows ? (unsigned) n_ind : kMaxBoxRows; }
-  __host__ __device__ static unsigned boxes_y(uint64_t n_ind) { return (unsigned) ((n_ind + kMaxBoxRows - 1) / kMaxBoxRows); }
+  __host__ __device__ static unsigned boxes_y(uint64_t n_ind) { return n_ind > kMaxBoxRows ? 2u : 1u; }   // warp shapes hold n_ind <= 512
+  __host__ __device__ static unsigned box_rows(uint64_t n_ind) { return (unsigned) ((n_ind + boxes_y(n_ind) - 1) / boxes_y(n_ind)); }
   __host__ __device__ static size_t region_bytes(uint64_t n_ind) { return ((size_t) box_rows(n_ind) * kInnerBytes + kAlign - 1) / kAlign * kAlign; }
   __host__ __device__ static size_t tile_bytes(uint64_t n_ind) { return 4 * kBoxesX * boxes_y(n_ind) * region_bytes(n_ind); }
-  // byte offset of (plane, individual i, site s of the CTA tile) inside a tile buffer (kAlign-aligned)
-  __device__ static size_t offset(unsigned plane, unsigned i, unsigned s, uint64_t n_ind) {
-    const unsigned region = (plane * kBoxesX + s / kInner) * boxes_y(n_ind) + i / kMaxBoxRows;
-    unsigned off = (i % kMaxBoxRows) * kInnerBytes + (s % kInner) * 8;
+  // byte offset of (plane, individual i, site s of the CTA tile) inside a tile buffer (kAlign-aligned);
+  // rows = box_rows, by = boxes_y, region = region_bytes of the tile (hoisted by the caller)
+  __device__ static unsigned offset(unsigned plane, unsigned i, unsigned s, unsigned rows, unsigned by, unsigned region) {
+    const unsigned y = i >= rows ? 1u : 0u;          // n_ind <= 512: at most two boxes of rows
+    unsigned off = (i - y * rows) * kInnerBytes + (s % kInner) * 8;
     off ^= ((off >> 7) & kSwizzleMask) << 4;
-    return region * region_bytes(n_ind) + off;
+    return ((plane * kBoxesX + s / kInner) * by + y) * region + off;
   }
   // per warp and individual: running product of e0 (mantissa in [1,2) as double + exponent as int)
   __host__ __device__ static size_t acc_doubles(uint64_t n_ind_pad) { return (((size_t) (kFreqThreads / 32) * n_ind_pad * 3 / 2 + 15) / 16) * 16; }
@@ -215,9 +216,11 @@ template <int G> struct FreqTile {
 // predication on it (converged sites simply keep iterating, their frequency was latched when they
 // stopped), the running (den - num) is accumulated directly so the next odds need one FMA and one
 // reciprocal after the reduction, and the stop test + vote hang off the side of the chain.
-template <int G, int K, bool PREFETCH, int OCC = freq_occupancy(K)>
+// MODE 0: no prefetch; 1: prefetch, accumulators in shared memory; 2: prefetch, accumulators in global scratch
+template <int G, int K, int MODE, int OCC = freq_occupancy(K)>
 __global__ void __launch_bounds__(kFreqThreads, OCC)
 freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
+  constexpr bool PREFETCH = MODE != 0, ACC_GLOBAL = MODE == 2;
   using Tile = FreqTile<G>;
   constexpr int kSitesPerWarp = Tile::kSitesPerWarp;
   constexpr int kSitesPerCta = Tile::kSitesPerCta;
@@ -225,8 +228,10 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane & (G - 1), sub = lane / G;
   extern __shared__ __align__(128) double freq_smem[];
-  double *mant_acc = freq_smem;                                              // [warps][n_ind_pad]
-  int *expo_acc = reinterpret_cast<int *>(freq_smem + (size_t) kWarps * A.n_ind_pad);   // [warps][n_ind_pad]
+  // accumulators [warps][n_ind_pad]: shared memory, or - when the tile buffers need all of it - this CTA's
+  // slice of a global scratch array (touched once per tile, latency hidden by the next tile's passes)
+  double *mant_acc = ACC_GLOBAL ? A.acc_scratch + (size_t) blockIdx.x * Tile::acc_doubles(A.n_ind_pad) : freq_smem;
+  int *expo_acc = reinterpret_cast<int *>(mant_acc + (size_t) kWarps * A.n_ind_pad);
   for (unsigned i = threadIdx.x; i < kWarps * A.n_ind_pad; i += kFreqThreads) { mant_acc[i] = 1.0; expo_acc[i] = 0; }
   double *my_mant = mant_acc + (size_t) warp * A.n_ind_pad;
   int *my_expo = expo_acc + (size_t) warp * A.n_ind_pad;
@@ -234,19 +239,20 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
   // ---- prefetch machinery: two tile buffers (aligned to the swizzle period), one mbarrier each
   const unsigned n_planes = A.post ? 4u : 3u;
   const size_t buf_bytes = Tile::tile_bytes(A.n_ind);
+  const unsigned box_rows = Tile::box_rows(A.n_ind), boxes_y = Tile::boxes_y(A.n_ind);
+  const unsigned region_bytes = (unsigned) Tile::region_bytes(A.n_ind);
   unsigned char *bufs = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(freq_smem + Tile::acc_doubles(A.n_ind_pad)) + Tile::kAlign - 1) & ~(uintptr_t) (Tile::kAlign - 1));
+      (reinterpret_cast<uintptr_t>(freq_smem + (ACC_GLOBAL ? 0 : Tile::acc_doubles(A.n_ind_pad))) + Tile::kAlign - 1) &
+      ~(uintptr_t) (Tile::kAlign - 1));
   __shared__ alignas(8) uint64_t bars[2];
   auto issue_tile = [&](unsigned t, int b) {      // thread 0 only
-    const unsigned by = Tile::boxes_y(A.n_ind);
-    const uint32_t box_bytes = Tile::box_rows(A.n_ind) * Tile::kInnerBytes;
-    mbar_arrive_expect_tx(&bars[b], n_planes * Tile::kBoxesX * by * box_bytes);
+    mbar_arrive_expect_tx(&bars[b], n_planes * Tile::kBoxesX * boxes_y * box_rows * Tile::kInnerBytes);
     const int first_site = (int) (t * kSitesPerCta);
     for (unsigned p = 0; p < n_planes; p++)
       for (unsigned bx = 0; bx < (unsigned) Tile::kBoxesX; bx++)
-        for (unsigned y = 0; y < by; y++)
-          tma_load_2d(bufs + (size_t) b * buf_bytes + ((p * Tile::kBoxesX + bx) * by + y) * Tile::region_bytes(A.n_ind),
-                      &A.maps[p], first_site + (int) bx * Tile::kInner, (int) (y * Tile::kMaxBoxRows), &bars[b]);
+        for (unsigned y = 0; y < boxes_y; y++)
+          tma_load_2d(bufs + (size_t) b * buf_bytes + ((p * Tile::kBoxesX + bx) * boxes_y + y) * region_bytes,
+                      &A.maps[p], first_site + (int) bx * Tile::kInner, (int) (y * box_rows), &bars[b]);
   };
   if (PREFETCH) {
     if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
@@ -263,7 +269,8 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
     const uint64_t sl = site_ok ? site : 0;
     const unsigned char *tile_buf = bufs + (size_t) (round & 1) * buf_bytes;
     auto staged = [&](unsigned plane, uint64_t i) {
-      return *reinterpret_cast<const double *>(tile_buf + Tile::offset(plane, (unsigned) i, (unsigned) site_in_cta, A.n_ind));
+      return *reinterpret_cast<const double *>(
+          tile_buf + Tile::offset(plane, (unsigned) i, (unsigned) site_in_cta, box_rows, boxes_y, region_bytes));
     };
     if (PREFETCH) {
       // the other buffer was last read before the __syncthreads that ended the previous tile
@@ -661,6 +668,13 @@ static bool pick_team_shape(uint64_t n_ind, int &W, int &K) {
   return false;
 }
 
+// Global scratch for the log e0 accumulators of every CTA the grid can have (needed when the tile buffers
+// leave no shared memory for them): [grid][warps or teams <= 8][n_ind_pad] x (double + int), rounded up.
+size_t freq_acc_scratch_bytes(uint64_t n_ind, uint64_t n_ind_pad, int sm_count) {
+  if (n_ind <= 128) return 0;
+  return (size_t) sm_count * 4 * ((8 * n_ind_pad * 3 / 2 + 15) / 16 * 16) * sizeof(double);
+}
+
 unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   int G, K, W;
   unsigned per_cta = 0;
@@ -683,14 +697,16 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   // all resident CTAs of an SM must fit their double buffers in its 228 KB of shared memory (1 KB reserved each)
   const size_t smem_cap = (size_t) 228 * 1024 / freq_occupancy(K) - 1024 - 256;
   const size_t bufs = 2 * FreqTile<G>::tile_bytes(a.n_ind) + FreqTile<G>::kAlign;   // + alignment slack
-  const bool prefetch = a.use_maps && acc + bufs <= smem_cap && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
+  const bool want = a.use_maps && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_warp<G, K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
+    cudaFuncSetAttribute(freq_emission_warp<G, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
+    cudaFuncSetAttribute(freq_emission_warp<G, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
     attr_done = true;
   }
-  if (prefetch) freq_emission_warp<G, K, true><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
-  else freq_emission_warp<G, K, false><<<grid, kFreqThreads, acc, st>>>(a, tiles);
+  if (want && acc + bufs <= smem_cap) freq_emission_warp<G, K, 1><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
+  else if (want && a.acc_scratch && bufs <= smem_cap) freq_emission_warp<G, K, 2><<<grid, kFreqThreads, bufs, st>>>(a, tiles);
+  else freq_emission_warp<G, K, 0><<<grid, kFreqThreads, acc, st>>>(a, tiles);
 }
 
 // Tensor maps of the four planes for the lane-group shape n_ind selects: [n_ind_pad][site_block] FP64,

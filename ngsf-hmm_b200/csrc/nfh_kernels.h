@@ -71,6 +71,7 @@ struct FreqArgs {
   unsigned long long *pass_total; // += sum over sites of the est_maf passes each site needed (bench.py's flop count)
   uint64_t n_ind, n_ind_pad, site_block, sites_owned;
   int update_freq;                // 1: run est_maf; 0: keep freq
+  double *acc_scratch;            // global home of the per-(CTA, warp|team, individual) log e0 accumulators, or NULL
   int use_maps;                   // tensor maps below are valid (freq_emission_warp prefetches through them)
   alignas(64) CUtensorMap maps[4];   // GL0, GL1, GL2, posterior planes as [n_ind_pad][site_block] tensors, see nfh_freq.cu
 };
@@ -90,6 +91,7 @@ void launch_estep(const EstepArgs &a, cudaStream_t st);
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st);
 // returns the grid size used (rows of loge0_part)
 void launch_fill(double *dst, double value, size_t n, cudaStream_t st);
+size_t freq_acc_scratch_bytes(uint64_t n_ind, uint64_t n_ind_pad, int sm_count);   // 0: never needed
 bool freq_tensor_maps(FreqArgs &a, const double *post_plane);   // fills a.maps / a.use_maps for the shape of a.n_ind
 unsigned freq_grid_size(const FreqArgs &a, int sm_count);
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st);
