@@ -380,6 +380,190 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Hybrid variant (used for 512 < n_ind <= 832): G lanes share a site and every lane keeps
+// K = kHybridRegK + KS individuals - the first kHybridRegK in registers, the other KS in
+// shared memory (its own column, read once per pass, conflict-free).  Keeping the lane
+// group small is what matters at large n_ind: the per-pass tail (lane reduction, division,
+// stop test) is paid per warp, so a warp should carry as many individual-passes as it can;
+// spreading the individuals over more lanes (G = 32 registers-only, or teams of warps)
+// leaves the FP64 pipe half idle behind 5 shuffle levels and a barrier per pass.  The price
+// is 48 bytes of shared-memory reads per stored individual and pass, about what an SM can
+// deliver beside the FP64 work.
+// ---------------------------------------------------------------------------
+constexpr int kHybridRegK = 12;
+constexpr int kHybridMaxKS = 14;
+
+// partial sums of the KS shared-memory individuals of this lane (same algebra as pass_sums)
+template <int KS>
+__device__ __forceinline__ void hybrid_sums(const double *__restrict__ coef, double t, double &A1, double &A2, double &A3) {
+  constexpr int kStride = kFreqThreads;          // doubles between consecutive coefficient planes
+#pragma unroll
+  for (int j0 = 0; j0 < KS; j0 += 4) {
+    constexpr int kFull4 = 4;
+    const int n = KS - j0 < kFull4 ? KS - j0 : kFull4;
+    double S[4], inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j < n) {
+        const double *c = coef + (size_t) (j0 + j) * 6 * kStride;
+        S[j] = fma(fma(c[kStride], t, c[2 * kStride]), t, c[0]);      // planes: a0, a2, h, na, nv, dz
+      } else {
+        S[j] = 1.0;
+      }
+    }
+    reciprocals<4>(S, inv);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j < n) {
+        const double *c = coef + (size_t) (j0 + j) * 6 * kStride;
+        A1 = fma(c[3 * kStride], inv[j], A1);
+        A2 = fma(c[4 * kStride], inv[j], A2);
+        A3 = fma(c[5 * kStride], inv[j], A3);
+      }
+    }
+  }
+}
+
+template <int G, int KS>
+__global__ void __launch_bounds__(kFreqThreads, 2)
+freq_emission_hybrid(FreqArgs A, unsigned n_site_tiles) {
+  constexpr int KR = kHybridRegK, K = KR + KS;
+  constexpr int kSitesPerWarp = 32 / G;
+  constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
+  constexpr int kWarps = kFreqThreads / 32;
+  constexpr int kStride = kFreqThreads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane & (G - 1), sub = lane / G;
+  extern __shared__ __align__(16) double hybrid_smem[];        // [KS * 6][kFreqThreads]
+  double *coef = hybrid_smem + threadIdx.x;
+  // log e0 accumulators of this CTA in global scratch (see freq_emission_warp, MODE 2)
+  const size_t acc_doubles = (((size_t) kWarps * A.n_ind_pad * 3 / 2 + 15) / 16) * 16;
+  double *mant_acc = A.acc_scratch + (size_t) blockIdx.x * acc_doubles;
+  int *expo_acc = reinterpret_cast<int *>(mant_acc + (size_t) kWarps * A.n_ind_pad);
+  for (unsigned i = threadIdx.x; i < kWarps * A.n_ind_pad; i += kFreqThreads) { mant_acc[i] = 1.0; expo_acc[i] = 0; }
+  __syncthreads();
+  double *my_mant = mant_acc + (size_t) warp * A.n_ind_pad;
+  int *my_expo = expo_acc + (size_t) warp * A.n_ind_pad;
+  unsigned my_passes = 0;
+
+  for (unsigned tile = blockIdx.x; tile < n_site_tiles; tile += gridDim.x) {
+    const uint64_t site = (uint64_t) tile * kSitesPerCta + warp * kSitesPerWarp + sub;
+    const bool site_ok = site < A.sites_owned;
+    const uint64_t sl = site_ok ? site : 0;
+
+    // ---- set-up: loads first, coefficients second; register part, then the shared-memory part
+    double a0[KR], a2[KR], hh[KR], na[KR], nv[KR], dz[KR];
+#pragma unroll
+    for (int k = 0; k < KR; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      const size_t at = (size_t) (i < A.n_ind ? i : 0) * A.site_block + sl;
+      a0[k] = A.gl0[at]; hh[k] = A.gl1[at]; a2[k] = A.gl2[at];
+      na[k] = A.post ? A.post[at] : 0.0;
+    }
+    double g_sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < KR; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      const IndCoef c = i < A.n_ind ? make_coef(a0[k], hh[k], a2[k], na[k]) : null_coef();
+      a0[k] = c.a0; a2[k] = c.a2; hh[k] = c.h; na[k] = c.na; nv[k] = c.nv; dz[k] = c.da - c.na;
+      g_sum += c.g;
+    }
+#pragma unroll
+    for (int j = 0; j < KS; j++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * (KR + j);
+      IndCoef c = null_coef();
+      if (i < A.n_ind) {
+        const size_t at = (size_t) i * A.site_block + sl;
+        c = make_coef(A.gl0[at], A.gl1[at], A.gl2[at], A.post ? A.post[at] : 0.0);
+      }
+      double *dst = coef + (size_t) j * 6 * kStride;
+      dst[0] = c.a0; dst[kStride] = c.a2; dst[2 * kStride] = c.h;
+      dst[3 * kStride] = c.na; dst[4 * kStride] = c.nv; dst[5 * kStride] = c.da - c.na;
+      g_sum += c.g;
+    }
+
+    double freq = A.update_freq ? kStartFreq : A.freq[sl];
+    if (A.update_freq) {
+#pragma unroll
+      for (int m = 1; m < G; m <<= 1) g_sum += __shfl_xor_sync(kFull, g_sum, m);
+      double num = 0.0, dmn_next = g_sum;
+      double odds = kStartOdds, prev = kStartFreq;
+      bool active = site_ok;
+      int passes = 0, site_passes = 0;
+      double S[KR];
+      pass_denominators<KR>(a0, a2, hh, odds, S);
+      do {
+        // register individuals
+        double inv[KR];
+        reciprocals<KR>(S, inv);
+        double A1 = 0.0, A2 = 0.0, A3 = 0.0, B1 = 0.0, B2 = 0.0, B3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < KR; k++) {
+          if (k & 1) { B1 = fma(na[k], inv[k], B1); B2 = fma(nv[k], inv[k], B2); B3 = fma(dz[k], inv[k], B3); }
+          else       { A1 = fma(na[k], inv[k], A1); A2 = fma(nv[k], inv[k], A2); A3 = fma(dz[k], inv[k], A3); }
+        }
+        // shared-memory individuals
+        hybrid_sums<KS>(coef, odds, B1, B2, B3);
+        const double s2 = A2 + B2;
+        double X = fma(odds, s2, A1 + B1), Z = fma(-odds, s2, A3 + B3);
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) {
+          X += __shfl_xor_sync(kFull, X, m);
+          Z += __shfl_xor_sync(kFull, Z, m);
+        }
+        num = fma(odds, X, num);
+        const double dmn = fmax(fma(odds, Z, dmn_next), num * kMinOddsInv);
+        odds = num * rcp_pos(dmn);
+        pass_denominators<KR>(a0, a2, hh, odds, S);      // next pass, ahead of the stop test
+        dmn_next = dmn + g_sum;
+        const double now = num * rcp_pos<true>(num + dmn);
+        passes++;
+        freq = active ? now : freq;
+        site_passes = active ? passes : site_passes;
+        active = active && (fabs(prev - now) > kEps) && (passes <= 100);   // gen_func.cpp:1006
+        prev = now;
+      } while (__any_sync(kFull, active));
+      if (site_ok && grp == 0) { A.freq[site] = freq; my_passes += site_passes; }
+    }
+
+    // ---- emission refresh (L1 is re-read: the coefficients fold it with F)
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint64_t i = (uint64_t) grp + (uint64_t) G * k;
+      double pe0 = 1.0;
+      if (i < A.n_ind && site_ok) {
+        const size_t at = (size_t) i * A.site_block + site;
+        const double L0 = k < KR ? a0[k < KR ? k : 0] : coef[(size_t) (k - KR) * 6 * kStride];
+        const double L2 = k < KR ? a2[k < KR ? k : 0] : coef[(size_t) ((k - KR) * 6 + 1) * kStride];
+        double e0, e1;
+        emissions(L0, A.gl1[at], L2, freq, e0, e1);
+        *emis_slot(A, i, site) = e1 * rcp_pos<true>(e0);
+        if (A.e0) A.e0[at] = e0;
+        pe0 = e0;
+      }
+#pragma unroll
+      for (int m = G; m < 32; m <<= 1) pe0 *= __shfl_xor_sync(kFull, pe0, m);
+      if (sub == 0 && i < A.n_ind_pad) {
+        int e;
+        my_mant[i] = split_exponent(my_mant[i] * pe0, e);
+        my_expo[i] += e;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) my_passes += __shfl_xor_sync(kFull, my_passes, m);
+  if (lane == 0 && my_passes) atomicAdd(A.pass_total, (unsigned long long) my_passes);
+  for (unsigned i = threadIdx.x; i < A.n_ind_pad; i += kFreqThreads) {
+    double m = 1.0;
+    int e = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) { m *= mant_acc[(size_t) w * A.n_ind_pad + i]; e += expo_acc[(size_t) w * A.n_ind_pad + i]; }
+    A.loge0_part[(size_t) blockIdx.x * A.n_ind_pad + i] = fma((double) e, 0.6931471805599453, log(m));
+  }
+}
+
 // Teams of W warps share one site (32 W lanes, K individuals per lane): the
 // register-resident scheme for 512 < n_ind <= 4096, e.g. the frequency side of
 // a multi-rank run, which always sees ALL individuals.  Per pass the lanes of a
@@ -658,6 +842,17 @@ static bool pick_shape(uint64_t n_ind, int &G, int &K) {
   return best_g != 0;
 }
 
+// Hybrid variant (G = 32): 512 < n_ind <= 32 (kHybridRegK + kHybridMaxKS) = 832, where it beats two-warp teams
+// (13.9 vs 15.1 ms at 800 individuals x 125,000 sites).  With fewer individuals the register-only shapes with
+// their tile prefetch are faster (200: 10.4 vs 12.6 ms, 400: 11.4 vs 13.4 ms).
+static bool pick_hybrid_shape(uint64_t n_ind, int &G, int &KS) {
+  if (getenv("NFH_FREQ_NO_HYBRID")) return false;
+  const int k = (int) ((n_ind + 31) / 32);
+  if (n_ind <= 512 || k > kHybridRegK + kHybridMaxKS) return false;
+  G = 32; KS = k - kHybridRegK;
+  return true;
+}
+
 // Team variant: fewest warps per site W in {2,4,8} with K = ceil(n / 32W) <= 13 (else <= 16).
 static bool pick_team_shape(uint64_t n_ind, int &W, int &K) {
   for (int cap : {13, kMaxK})
@@ -679,7 +874,9 @@ unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   int G, K, W;
   unsigned per_cta = 0;
   unsigned ctas_per_sm = 4;
-  if (pick_shape(a.n_ind, G, K)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = freq_occupancy(K); }
+  int KS;
+  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = 2; }
+  else if (pick_shape(a.n_ind, G, K)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = freq_occupancy(K); }
   else if (pick_team_shape(a.n_ind, W, K)) per_cta = ((W <= 4 ? 128 : 256) / 32) / W;
   if (per_cta) {
     unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
@@ -797,8 +994,37 @@ static bool dispatch_team_k(int K, const FreqArgs &a, unsigned grid, cudaStream_
   }
 }
 
+template <int G, int KS>
+static void launch_hybrid_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
+  const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
+  const size_t smem = (size_t) KS * 6 * kFreqThreads * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(freq_emission_hybrid<G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    attr_done = true;
+  }
+  freq_emission_hybrid<G, KS><<<grid, kFreqThreads, smem, st>>>(a, tiles);
+}
+
+template <int G>
+static bool dispatch_hybrid(int KS, const FreqArgs &a, unsigned grid, cudaStream_t st) {
+  switch (KS) {
+#define NFH_CASE(k) case k: launch_hybrid_variant<G, k>(a, grid, st); return true;
+    NFH_CASE(5) NFH_CASE(6) NFH_CASE(7) NFH_CASE(8) NFH_CASE(9) NFH_CASE(10)
+    NFH_CASE(11) NFH_CASE(12) NFH_CASE(13) NFH_CASE(14)
+#undef NFH_CASE
+    default: return false;
+  }
+}
+
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  int G, K, W;
+  int G, K, W, KS;
+  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS)) {
+    bool ok = false;
+    if (G == 32) ok = dispatch_hybrid<32>(KS, a, grid, st);
+    if (ok) return 1;
+  }
   if (pick_shape(a.n_ind, G, K)) {
     bool ok = false;
     switch (G) {

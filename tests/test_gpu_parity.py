@@ -125,10 +125,15 @@ def test_freq_update_matches_oracle(oracle, N, S, seed):
         _posterior_check(ctx.get_posterior(), marg2)
 
 
-@pytest.mark.parametrize("N,S", [(150, 300), (600, 48), (1100, 40), (4200, 12)],
-                         ids=["warp-G32", "team-W2", "team-W4", "stream"])
-def test_freq_update_large_n_variants(oracle, N, S):
-    """More individuals than one lane group holds: 32-lane groups, teams of warps, and the streaming path."""
+@pytest.mark.parametrize("N,S,no_hybrid", [(150, 300, 0), (450, 64, 0), (600, 48, 0), (820, 40, 0), (600, 48, 1),
+                                           (1100, 40, 0), (4200, 12, 0)],
+                         ids=["warp-G16", "warp-G32-global-acc", "hybrid-K19", "hybrid-K26", "team-W2", "team-W4",
+                              "stream"])
+def test_freq_update_large_n_variants(oracle, monkeypatch, N, S, no_hybrid):
+    """More individuals than one 8-lane group holds: wider lane groups (tile prefetch with accumulators in
+    shared memory or global scratch), the register + shared-memory hybrid, teams of warps, the streaming path."""
+    if no_hybrid:
+        monkeypatch.setenv("NFH_FREQ_NO_HYBRID", "1")
     d, ctx = _setup(N, S, 31, freq=(0.05, 0.5), indF=(0.0, 0.5))
     with ctx:
         gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.1, 0.1, 0.2)
