@@ -507,6 +507,7 @@ int nfh_viterbi(nfh_ctx *ctx, char *path_out) {
   const size_t n_chunks = (size_t) ctx->n_tiles * kScanThreads;
   if (!ctx->vit_work) {
     NFH_CUDA(cudaMalloc((void **) &ctx->vit_work, ctx->n_loc * stride));
+    NFH_CUDA(cudaMemsetAsync(ctx->vit_work, 0, ctx->n_loc * stride, ctx->stream));   // padding bytes of the last tile
     NFH_CUDA(cudaMalloc((void **) &ctx->vit_maps, ctx->n_loc * (n_chunks + 2 * (size_t) ctx->n_tiles)));
     NFH_CUDA(cudaMalloc((void **) &ctx->vit_tile_prod, ctx->n_loc * ctx->n_tiles * sizeof(double4)));
     NFH_CUDA(cudaMalloc((void **) &ctx->vit_final, ctx->n_loc * sizeof(int)));
