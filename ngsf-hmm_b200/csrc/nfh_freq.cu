@@ -391,7 +391,7 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
 // is 48 bytes of shared-memory reads per stored individual and pass, about what an SM can
 // deliver beside the FP64 work.
 // ---------------------------------------------------------------------------
-constexpr int kHybridRegK = 12;
+constexpr int kHybridRegK = 12;      // 9 gave the same time: the compiler fills 255 registers either way
 constexpr int kHybridMaxKS = 14;
 
 // partial sums of the KS shared-memory individuals of this lane (same algebra as pass_sums)
