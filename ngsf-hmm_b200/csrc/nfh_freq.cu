@@ -78,7 +78,7 @@ __device__ __forceinline__ IndCoef null_coef() {   // padding slot: contributes 
   return k;
 }
 
-// 9 FP64 instructions + 1 MUFU, no branches.
+// u/v/a form used by the streaming path: 9 FP64 instructions + 1 MUFU, no branches.
 __device__ __forceinline__ void accumulate(const IndCoef &k, double u, double v, double a, double &A1, double &A2,
                                            double &A3) {
   const double S = fma(k.a0, u, fma(k.a2, v, k.h * a));
@@ -207,7 +207,7 @@ template <int G> struct FreqTile {
 // G lanes share one site (G divides 32); each lane keeps K individuals.
 //
 // PREFETCH: the CTA's next site tile (GL x3 + posterior rows of all individuals, 16-32 sites wide)
-// is fetched into shared memory by TMA bulk copies while the current tile runs its ~101 passes, so
+// is fetched into shared memory by TMA tensor copies while the current tile runs its ~101 passes, so
 // the set-up of a tile reads shared memory instead of waiting on HBM (ncu r01c: long-scoreboard
 // stalls were 18 % of the kernel).  Two buffers, one mbarrier each.
 //
