@@ -335,3 +335,28 @@ def test_full_size_properties_without_oracle():
         sure = post > 0.999
         assert (path[sure] == 1).mean() > 0.99
     del torch
+
+
+def test_error_statuses_follow_the_reference(oracle):
+    """Conditions the reference turns into error()/exit: NaN in a recursion, an estimation
+    method it cannot run, arguments outside the context geometry; NaN/Inf objective parameters return
+    -1e15 (EM.cpp:454-456)."""
+    d, ctx = _setup(4, 600, 9)
+    with ctx:
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.1, 0.1, 0.2)
+        out = ctx.lkl_batch(np.array([0, 0, 1], dtype=np.int32), np.array([0.1, np.nan, 0.2]),
+                            np.array([0.2, 0.2, np.inf]))
+        assert np.isfinite(out[0]) and out[1] == -1e15 and out[2] == -1e15
+        with pytest.raises(nfh.NfhError) as err:
+            ctx.freq_update(2)
+        assert err.value.status == 2 and "MAF estimation method" in str(err.value)
+        with pytest.raises(nfh.NfhError) as err:
+            ctx.upload_gl(np.zeros((10, 4, 3)), first_site=595)
+        assert err.value.status == 2
+        bad = np.ascontiguousarray(np.transpose(gl_ind, (1, 0, 2))).copy()
+        bad[300, 2, :] = np.nan
+        ctx.upload_gl(bad)
+        ctx.emission_refresh()
+        with pytest.raises(nfh.NfhError) as err:
+            ctx.estep()
+        assert err.value.status == 3 and "invalid Lkl" in str(err.value)
