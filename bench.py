@@ -346,6 +346,8 @@ def main():
         roof_freq = {"kernel": "freq_emission_warp", "bound": "fp64", "achieved": freq_tf,
                      "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": freq_tf / (fp64_peak / 1e12),
                      "traffic": t_freq, "passes_per_site": passes_per_site,
+                     "bound_note": "FP64 CUDA-core pipe (DFMA), not tensor cores: the work is per-individual rational "
+                                   "functions with no dense contraction",
                      "instruction_mix_ceiling": FREQ_FLOPS_PER_IND_PASS / (2 * FREQ_INSTR_PER_IND_PASS),
                      "operand_fetch_note": "DFMA with 3 register operands issues every 3.06 cycles, not 2 "
                                            "(profiles/microbench/fp64_operands.cu)", "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
