@@ -115,6 +115,14 @@ int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out);
 int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
                   double *neg_lkl_out);
 
+/* nfh_estep and the first nfh_lkl_batch of an EM iteration in one call.  findmax_bfgs starts at the
+ * parameters the E-step has just used (EM.cpp:151-205), so its first objective evaluation is the E-step's
+ * forward recursion: when the first request of every owned individual (individuals in order 0..n_ind_owned-1,
+ * all present) is its current (F, alpha), the forward products of that point also feed the posterior and
+ * the E-step's own product kernel is skipped.  Same outputs as the two calls. */
+int nfh_estep_with_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
+                         double *neg_lkl_out, double *ind_lkl_out);
+
 /* Replaces: the freq/emission site loop (EM.cpp:224-271) = est_maf
  * (gen_func.cpp:974-1009) + calc_emission.  method 1 = per-site EM (the only
  * method the reference can run, SURVEY.md finding 4); method 0 = keep freq,

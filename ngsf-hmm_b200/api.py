@@ -28,7 +28,7 @@ EXPORTS = [
     "nfh_upload_gl", "nfh_upload_pos_dist", "nfh_set_freq", "nfh_get_freq", "nfh_set_ind_params",
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
-    "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister",
+    "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister", "nfh_estep_with_batch",
 ]
 
 
@@ -83,6 +83,8 @@ def load_library():
     L.nfh_emission_refresh.restype = cint; L.nfh_emission_refresh.argtypes = [_vp, cint]
     L.nfh_estep.restype = cint; L.nfh_estep.argtypes = [_vp, _dp]
     L.nfh_lkl_batch.restype = cint; L.nfh_lkl_batch.argtypes = [_vp, u64, C.POINTER(i32), _dp, _dp, _dp]
+    L.nfh_estep_with_batch.restype = cint
+    L.nfh_estep_with_batch.argtypes = [_vp, u64, C.POINTER(i32), _dp, _dp, _dp, _dp]
     L.nfh_freq_update.restype = cint; L.nfh_freq_update.argtypes = [_vp, cint, cint, _dp]
     L.nfh_viterbi.restype = cint; L.nfh_viterbi.argtypes = [_vp, _vp]
     L.nfh_get_posterior.restype = cint; L.nfh_get_posterior.argtypes = [_vp, _dp]
@@ -210,6 +212,14 @@ class Context:
         self._chk(self.L.nfh_lkl_batch(self.h, len(ind), ind.ctypes.data_as(C.POINTER(C.c_int32)), _p(F), _p(a),
                                        _p(out)))
         return out
+
+    def estep_with_batch(self, ind, F, alpha):
+        """E-step + first objective batch in one call; returns (neg_lkl of the requests, ind_lkl)."""
+        ind = np.ascontiguousarray(ind, dtype=np.int32); F = _f64(F); a = _f64(alpha)
+        out = np.empty(len(ind)); lk = np.empty(self.n_ind_owned)
+        self._chk(self.L.nfh_estep_with_batch(self.h, len(ind), ind.ctypes.data_as(C.POINTER(C.c_int32)), _p(F), _p(a),
+                                              _p(out), _p(lk)))
+        return out, lk
 
     def pinned_empty(self, n):
         """float64 host array of n elements, page-locked until the context is closed (full-speed copies)."""

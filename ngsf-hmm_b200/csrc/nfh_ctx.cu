@@ -65,6 +65,7 @@ struct nfh_ctx {
   double *h_small = nullptr;       // 8 * max(n_loc, 16) doubles + requests
   size_t h_small_doubles = 0;
   LklGroup *h_groups = nullptr;
+  std::vector<double> h_indF, h_alpha;   // host mirror of the parameters last set (nfh_estep_with_batch checks against it)
   int *h_status = nullptr;
   void *h_stage = nullptr, *d_stage = nullptr;
 
@@ -349,6 +350,8 @@ int nfh_get_freq(nfh_ctx *ctx, double *freq) {
 }
 
 int nfh_set_ind_params(nfh_ctx *ctx, const double *indF, const double *alpha) {
+  ctx->h_indF.assign(indF, indF + ctx->n_owned);
+  ctx->h_alpha.assign(alpha, alpha + ctx->n_owned);
   NFH_CUDA(cudaSetDevice(ctx->device));
   double *h = ctx->h_small;
   NFH_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -416,19 +419,24 @@ int nfh_freq_update(nfh_ctx *ctx, int method, int posterior_is_zero, double *fre
   return NFH_OK;
 }
 
+static EstepArgs estep_args(nfh_ctx *ctx) {
+  EstepArgs a;
+  a.emis = ctx->emis_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
+  a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
+  a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
+  a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
+  a.post_peers.direct = ctx->peer_direct ? 1 : 0;
+  a.post_peers.rank = ctx->rank; a.post_peers.n_loc = ctx->n_loc;
+  for (int r = 0; r < kMaxRanks; r++) a.post_peers.base[r] = ctx->peer_post[r];
+  a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
+  a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
+  return a;
+}
+
 int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out) {
   NFH_CUDA(cudaSetDevice(ctx->device));
   if (ctx->n_owned) {
-    EstepArgs a;
-    a.emis = ctx->emis_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
-    a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
-    a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
-    a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
-    a.post_peers.direct = ctx->peer_direct ? 1 : 0;
-    a.post_peers.rank = ctx->rank; a.post_peers.n_loc = ctx->n_loc;
-    for (int r = 0; r < kMaxRanks; r++) a.post_peers.base[r] = ctx->peer_post[r];
-    a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
-    a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
+    const EstepArgs a = estep_args(ctx);
     {
       FamilyScope fs(ctx, kFamEstep, 3);
       launch_estep(a, ctx->stream);
@@ -445,9 +453,9 @@ int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out) {
   return NFH_OK;
 }
 
-int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
-                  double *neg_lkl_out) {
-  if (n_req == 0) return NFH_OK;
+// Shared body of nfh_lkl_batch and nfh_estep_with_batch.
+static int lkl_batch_impl(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
+                          double *neg_lkl_out, bool with_estep, double *ind_lkl_out) {
   if (n_req > ctx->n_loc * kMaxPoints) return fail(ctx, NFH_ERR_ARG, "nfh_lkl_batch: too many requests in one call");
   NFH_CUDA(cudaSetDevice(ctx->device));
   NFH_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned mirrors are reused
@@ -456,6 +464,7 @@ int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double
   for (uint64_t q = 0; q < n_req; q++) {
     if (ind[q] < 0 || (uint64_t) ind[q] >= ctx->n_owned) return fail(ctx, NFH_ERR_ARG, "nfh_lkl_batch: bad individual");
     if (std::isnan(F[q]) || std::isinf(F[q]) || std::isnan(alpha[q]) || std::isinf(alpha[q])) {
+      if (with_estep) return fail(ctx, NFH_ERR_ARG, "nfh_estep_with_batch: non-finite parameters");
       neg_lkl_out[q] = -1e15;   // EM.cpp:454-456
       continue;
     }
@@ -477,6 +486,17 @@ int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double
     while (gg.n_same < gg.npts && gg.alpha[gg.n_same] == gg.alpha[0]) gg.n_same++;
     gg.pad_ = 0;
   }
+  if (with_estep) {
+    // the first point of every owned individual, in order, must be the parameters the context holds
+    bool ok = n_groups == ctx->n_owned && ctx->h_indF.size() == ctx->n_owned;
+    for (uint32_t k = 0; ok && k < n_groups; k++) {
+      const LklGroup &gg = ctx->h_groups[k];
+      ok = gg.ind == (int) k && gg.F[0] == ctx->h_indF[k] && gg.alpha[0] == ctx->h_alpha[k];
+    }
+    if (!ok)
+      return fail(ctx, NFH_ERR_ARG,
+                  "nfh_estep_with_batch: the first request of every owned individual must be its current (F, alpha)");
+  }
   if (n_groups == 0) return NFH_OK;
   NFH_CUDA(cudaMemcpyAsync(ctx->groups, ctx->h_groups, n_groups * sizeof(LklGroup), cudaMemcpyHostToDevice,
                            ctx->stream));
@@ -485,19 +505,46 @@ int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double
   a.groups = ctx->groups; a.tile_prod = ctx->lkl_tile_prod; a.neg_lkl = ctx->neg_lkl;
   a.n_rows = ctx->n_loc; a.n_sites = ctx->n_sites; a.site_block = ctx->site_block;
   a.n_tiles = ctx->n_tiles; a.n_groups = n_groups;
+  a.emit_chunk_prod = with_estep ? ctx->chunk_prod : nullptr;
+  a.emit_tile_prod = with_estep ? ctx->tile_prod : nullptr;
   {
     FamilyScope fs(ctx, kFamLkl, 2);
     launch_lkl_batch(a, ctx->stream);
   }
+  if (with_estep) {
+    const EstepArgs ea = estep_args(ctx);
+    FamilyScope fs(ctx, kFamEstep, 2);
+    launch_estep_tail(ea, ctx->stream);
+  }
   NFH_CUDA(cudaGetLastError());
   NFH_CUDA(cudaMemcpyAsync(ctx->h_small, ctx->neg_lkl, n_req * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  NFH_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = NFH_OK;
+  if (with_estep) {
+    NFH_CUDA(cudaMemcpyAsync(ctx->h_small + n_req, ctx->ind_lkl, ctx->n_owned * sizeof(double), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    rc = sync_and_check(ctx);
+    if (ind_lkl_out) memcpy(ind_lkl_out, ctx->h_small + n_req, ctx->n_owned * sizeof(double));
+  } else {
+    NFH_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   for (uint32_t k = 0; k < n_groups; k++)
     for (int p = 0; p < ctx->h_groups[k].npts; p++) {
       int q = ctx->h_groups[k].out[p];
       neg_lkl_out[q] = ctx->h_small[q];
     }
-  return NFH_OK;
+  return rc;
+}
+
+int nfh_lkl_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
+                  double *neg_lkl_out) {
+  if (n_req == 0) return NFH_OK;
+  return lkl_batch_impl(ctx, n_req, ind, F, alpha, neg_lkl_out, false, nullptr);
+}
+
+int nfh_estep_with_batch(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, const double *F, const double *alpha,
+                         double *neg_lkl_out, double *ind_lkl_out) {
+  if (ctx->n_owned == 0) return NFH_OK;
+  return lkl_batch_impl(ctx, n_req, ind, F, alpha, neg_lkl_out, true, ind_lkl_out);
 }
 
 int nfh_viterbi(nfh_ctx *ctx, char *path_out) {

@@ -393,7 +393,8 @@ __host__ __device__ constexpr int lkl_split(int NS, int NA) {
 // layout is fixed per group, so the whole body is straight-line code.  Lane 0 of every warp leaves
 // the warp's ordered product in shared memory.
 template <int NS, int NA>
-__device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklSmem &sm, int t) {
+__device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklSmem &sm, int t,
+                                              double4 *__restrict__ emit_chunks) {
   constexpr int NP = NS + NA;
   constexpr int kBody = 6;
   const double *r = sm.r + t * kChunk;
@@ -435,6 +436,8 @@ __device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklS
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     e[p] += renorm(m[p]);
+    // the group's first point doubles as the E-step's forward product of this chunk (direction only)
+    if (p == 0 && first == 0 && emit_chunks) emit_chunks[t] = make_double4(m[0].a, m[0].b, m[0].c, m[0].d);
     warp_ordered_product(m[p], e[p]);
     double l = ls[p < NS ? 0 : 1 + (p - NS)];
 #pragma unroll
@@ -444,13 +447,14 @@ __device__ __forceinline__ void lkl_chunk_run(const LklGroup &g, int first, LklS
 }
 
 template <int NS, int NA>
-__device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, int half, int t) {
+__device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, int half, int t,
+                                                double4 *__restrict__ emit_chunks) {
   constexpr int k = lkl_split(NS, NA);
   constexpr int NSa = k < NS ? k : NS, NAa = k - NSa, NSb = NS - NSa, NAb = NA - NAa;
   if (half == 0) {
-    lkl_chunk_run<NSa, NAa>(g, 0, sm, t);
+    lkl_chunk_run<NSa, NAa>(g, 0, sm, t, emit_chunks);
   } else {
-    if constexpr (NSb + NAb > 0) lkl_chunk_run<NSb, NAb>(g, k, sm, t);
+    if constexpr (NSb + NAb > 0) lkl_chunk_run<NSb, NAb>(g, k, sm, t, nullptr);
   }
 }
 
@@ -460,7 +464,8 @@ __device__ __forceinline__ void lkl_tile_halves(const LklGroup &g, LklSmem &sm, 
 __global__ void __launch_bounds__(kLklThreads)
 lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ dist,
                   const LklGroup *__restrict__ groups, TileProd *__restrict__ tile_prod, uint64_t n_rows,
-                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles) {
+                  uint64_t n_sites, uint64_t site_block, uint32_t n_tiles, double4 *__restrict__ emit_chunk_prod,
+                  TileProd *__restrict__ emit_tile_prod) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   LklSmem &sm = *reinterpret_cast<LklSmem *>(smem_raw);
   const uint32_t tile = blockIdx.x, grp = blockIdx.y;
@@ -480,7 +485,9 @@ lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ di
   mbar_wait(&sm.bar, 0);
   const int half = threadIdx.x / kScanThreads, t = threadIdx.x % kScanThreads;
 
-#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_halves<ns, na>(g, sm, half, t); break;
+  double4 *emit_chunks =
+      emit_chunk_prod ? emit_chunk_prod + ((size_t) g.ind * n_tiles + tile) * kScanThreads : nullptr;
+#define NFH_LKL(ns, na) case (ns) * 8 + (na): lkl_tile_halves<ns, na>(g, sm, half, t, emit_chunks); break;
   switch (g.n_same * 8 + (g.npts - g.n_same)) {
     NFH_LKL(1, 0) NFH_LKL(1, 1) NFH_LKL(1, 2) NFH_LKL(1, 3) NFH_LKL(1, 4)
     NFH_LKL(2, 0) NFH_LKL(2, 1) NFH_LKL(2, 2) NFH_LKL(2, 3)
@@ -504,6 +511,7 @@ lkl_tile_products(const double *__restrict__ emis, const double *__restrict__ di
     TileProd out;
     out.a = acc.a; out.b = acc.b; out.c = acc.c; out.d = acc.d; out.e = (double) ae; out.l = al_sum;
     tile_prod[((size_t) grp * kMaxPoints + p) * n_tiles + tile] = out;
+    if (p == 0 && emit_tile_prod) emit_tile_prod[(size_t) g.ind * n_tiles + tile] = out;
   }
 }
 
@@ -568,11 +576,23 @@ void launch_estep(const EstepArgs &a, cudaStream_t st) {
                                                                   a.n_rows, a.n_sites, a.site_block, a.n_tiles);
 }
 
+void launch_estep_tail(const EstepArgs &a, cudaStream_t st) {
+  set_smem_attrs();
+  dim3 grid(a.n_tiles, (unsigned) a.n_rows_valid);
+  estep_tile_carries<<<(unsigned) ((a.n_rows_valid + 3) / 4), 128, 0, st>>>(
+      a.tile_prod, a.indF, a.loge0_sum, a.fwd_carry, a.bwd_carry, a.ind_lkl, a.status, (uint32_t) a.n_rows_valid,
+      a.n_tiles);
+  estep_chunk_apply<<<grid, kScanThreads, sizeof(TileSmem), st>>>(a.emis, a.dist, a.indF, a.alpha, a.chunk_prod,
+                                                                  a.fwd_carry, a.bwd_carry, a.post, a.post_peers, a.status,
+                                                                  a.n_rows, a.n_sites, a.site_block, a.n_tiles);
+}
+
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st) {
   set_smem_attrs();
   dim3 grid(a.n_tiles, a.n_groups);
   lkl_tile_products<<<grid, kLklThreads, sizeof(LklSmem), st>>>(a.emis, a.dist, a.groups, a.tile_prod, a.n_rows,
-                                                                 a.n_sites, a.site_block, a.n_tiles);
+                                                                 a.n_sites, a.site_block, a.n_tiles, a.emit_chunk_prod,
+                                                                 a.emit_tile_prod);
   const unsigned warps = a.n_groups * kMaxPoints;
   lkl_finish<<<(warps + 3) / 4, 128, 0, st>>>(a.tile_prod, a.groups, a.loge0_sum, a.neg_lkl, a.n_groups, a.n_tiles);
 }

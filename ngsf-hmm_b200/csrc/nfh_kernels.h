@@ -56,6 +56,11 @@ struct LklArgs {
   const LklGroup *groups;
   TileProd *tile_prod;       // [n_groups][kMaxPoints][n_tiles]
   double *neg_lkl;
+  // When set, point 0 of every group is also the E-step's forward product: its chunk products and tile
+  // products go to the E-step buffers (EstepArgs::chunk_prod / tile_prod, row = the group's individual),
+  // so that estep_chunk_products need not run (launch_estep_tail follows).
+  double4 *emit_chunk_prod;
+  TileProd *emit_tile_prod;
   uint64_t n_rows, n_sites, site_block;
   uint32_t n_tiles, n_groups;
 };
@@ -88,6 +93,7 @@ struct ViterbiArgs {
 };
 
 void launch_estep(const EstepArgs &a, cudaStream_t st);
+void launch_estep_tail(const EstepArgs &a, cudaStream_t st);   // carries + apply, products already in place
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st);
 // returns the grid size used (rows of loge0_part)
 void launch_fill(double *dst, double value, size_t n, cudaStream_t st);

@@ -81,8 +81,8 @@ double minimize_with_numeric_gradient(int n, double *x, objective_fn fun, const 
 }
 
 int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, bool F_fixed, bool alpha_fixed,
-                         BfgsStats *stats) {
-  if (F_fixed && alpha_fixed) return NFH_OK;
+                         BfgsStats *stats, double *estep_lkl_out) {
+  if (F_fixed && alpha_fixed) return estep_lkl_out ? nfh_estep(ctx, estep_lkl_out) : NFH_OK;
   const double inf_inv = 1.0 / 1e15;                 // 1/INF, EM.cpp:425
   struct Slot {
     std::unique_ptr<BoxLbfgs> opt;
@@ -108,6 +108,18 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
   std::vector<int32_t> req_ind;
   std::vector<double> req_F, req_a, req_out;
   BfgsStats local;
+  // the E-step rides on the first round when every individual takes part in it (always, unless an optimiser
+  // stops before its first evaluation)
+  bool estep_pending = estep_lkl_out != nullptr;
+  if (estep_pending) {
+    bool all_active = true;
+    for (uint64_t i = 0; i < n_ind; i++) all_active = all_active && slots[i].active;
+    if (!all_active) {
+      int rc = nfh_estep(ctx, estep_lkl_out);
+      if (rc != NFH_OK) return rc;
+      estep_pending = false;
+    }
+  }
   for (;;) {
     req_ind.clear(); req_F.clear(); req_a.clear();
     for (uint64_t i = 0; i < n_ind; i++) {
@@ -123,7 +135,14 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
     }
     if (req_ind.empty()) break;
     req_out.resize(req_ind.size());
-    int rc = nfh_lkl_batch(ctx, req_ind.size(), req_ind.data(), req_F.data(), req_a.data(), req_out.data());
+    int rc;
+    if (estep_pending) {
+      rc = nfh_estep_with_batch(ctx, req_ind.size(), req_ind.data(), req_F.data(), req_a.data(), req_out.data(),
+                                estep_lkl_out);
+      estep_pending = false;
+    } else {
+      rc = nfh_lkl_batch(ctx, req_ind.size(), req_ind.data(), req_F.data(), req_a.data(), req_out.data());
+    }
     if (rc != NFH_OK) return rc;
     local.rounds++;
     local.evaluations += req_ind.size();

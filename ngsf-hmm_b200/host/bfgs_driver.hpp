@@ -53,7 +53,10 @@ double minimize_with_numeric_gradient(int n, double *x, objective_fn fun, const 
 // for all individuals this context owns.  indF / alpha are updated in place.
 // Bounds: F in [1e-15, 1-1e-15], alpha in [1e-15, 10]; a fixed parameter
 // collapses its bounds to the current value.
+// With estep_lkl_out != nullptr the E-step of the same iteration (EM.cpp:151-185) is run here as well: the
+// first batched round goes through nfh_estep_with_batch (its centre points are the E-step's parameters),
+// or, when nothing is optimised, through nfh_estep; estep_lkl_out[n_ind] receives ind_lkl.
 int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, bool F_fixed, bool alpha_fixed,
-                         BfgsStats *stats);
+                         BfgsStats *stats, double *estep_lkl_out = nullptr);
 
 }  // namespace nfh_host

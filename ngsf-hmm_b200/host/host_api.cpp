@@ -3,6 +3,7 @@
 // bookkeeping and iteration order - driving the CUDA C ABI.
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "bfgs_driver.hpp"
 #include "ngsfhmm_host.h"
@@ -32,9 +33,15 @@ int nfh_host_em_iteration(nfh_ctx *ctx, double *indF, double *alpha, int F_fixed
   const uint64_t n = nfh_n_ind_owned(ctx);
   int rc = nfh_set_ind_params(ctx, indF, alpha);                 // parameters of the previous iteration
   if (rc != NFH_OK) return rc;
-  rc = nfh_estep(ctx, ind_lkl_out);                              // EM.cpp:151-185
-  if (rc != NFH_OK) return rc;
-  rc = nfh_host_bfgs_update(ctx, n, indF, alpha, F_fixed, alpha_fixed, stats_out);   // EM.cpp:188-205 (old emissions)
+  // E-step (EM.cpp:151-185) and F / alpha update (EM.cpp:188-205, old emissions): the optimiser starts at the
+  // E-step's parameters, so its first batched round and the E-step share one forward pass
+  std::vector<double> lkl_tmp;
+  if (!ind_lkl_out) { lkl_tmp.resize(n); ind_lkl_out = lkl_tmp.data(); }
+  BfgsStats st;
+  rc = bfgs_update_lockstep(ctx, n, indF, alpha, F_fixed != 0, alpha_fixed != 0, &st, ind_lkl_out);
+  if (stats_out) {
+    stats_out[0] = st.rounds; stats_out[1] = st.evaluations; stats_out[2] = st.max_rounds_one_individual;
+  }
   if (rc != NFH_OK) return rc;
   if (freq_est != 0) rc = nfh_freq_update(ctx, 1, 0, freq_out);  // EM.cpp:224-271 (new posterior)
   return rc;

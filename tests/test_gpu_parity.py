@@ -360,3 +360,33 @@ def test_error_statuses_follow_the_reference(oracle):
         with pytest.raises(nfh.NfhError) as err:
             ctx.estep()
         assert err.value.status == 3 and "invalid Lkl" in str(err.value)
+
+
+def test_estep_with_batch_equals_the_two_calls(oracle):
+    """nfh_estep_with_batch = nfh_estep + nfh_lkl_batch when every individual's first request is its current
+    (F, alpha): same objective values, same ind_lkl and posterior (the forward products are shared)."""
+    N, S = 7, 9000
+    d, ctx = _setup(N, S, 17, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    with ctx:
+        rng = np.random.default_rng(3)
+        F0 = rng.uniform(0.05, 0.6, N); a0 = rng.uniform(0.01, 2.0, N)
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.1, F0, a0)
+        lk1 = ctx.estep()
+        post1 = ctx.get_posterior()
+        ind, Fq, aq = [], [], []
+        for i in range(N):
+            eh = 3e-6
+            for dF, da in ((0, 0), (eh, 0), (-eh, 0), (0, eh), (0, -eh)):
+                ind.append(i); Fq.append(F0[i] + dF); aq.append(a0[i] + da)
+        want = ctx.lkl_batch(ind, Fq, aq)
+        got, lk2 = ctx.estep_with_batch(ind, Fq, aq)
+        post2 = ctx.get_posterior()
+        np.testing.assert_array_equal(got, want)
+        np.testing.assert_allclose(lk2, lk1, rtol=1e-13)
+        np.testing.assert_allclose(post2, post1, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(-got[0::5], lk1, rtol=1e-12)          # the centre point is the E-step's lkl
+        # a first request that is not the current parameter point is refused
+        Fq[5] += 1e-3
+        with pytest.raises(nfh.NfhError) as err:
+            ctx.estep_with_batch(ind, Fq, aq)
+        assert err.value.status == 2
