@@ -28,6 +28,12 @@ double nfh_host_minimize(int n, double *x, nfh_objective fun, const void *data, 
 int nfh_host_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed, int alpha_fixed,
                          uint64_t stats_out[3]);
 
+/* E-step + F / alpha update of one EM iteration (EM.cpp:151-205) for the parameters last set with
+ * nfh_set_ind_params: the optimiser's first batched round carries the E-step (nfh_estep_with_batch).
+ * ind_lkl_out[n_ind] = the E-step's log-likelihoods; indF / alpha are updated in place. */
+int nfh_host_estep_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed,
+                               int alpha_fixed, double *ind_lkl_out, uint64_t stats_out[3]);
+
 /* Replaces iter_EM (EM.cpp:139-289) on one rank: E-step with the given
  * parameters, F/alpha update against the old emissions, frequency update +
  * emission refresh with the new posteriors.  indF/alpha in/out [n_ind_owned];

@@ -34,6 +34,8 @@ def load_host_library():
         u64p = C.POINTER(C.c_uint64)
         L.nfh_host_bfgs_update.restype = C.c_int
         L.nfh_host_bfgs_update.argtypes = [C.c_void_p, C.c_uint64, _dp, _dp, C.c_int, C.c_int, u64p]
+        L.nfh_host_estep_bfgs_update.restype = C.c_int
+        L.nfh_host_estep_bfgs_update.argtypes = [C.c_void_p, C.c_uint64, _dp, _dp, C.c_int, C.c_int, _dp, u64p]
         L.nfh_host_em_iteration.restype = C.c_int
         L.nfh_host_em_iteration.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _dp, u64p]
         _hostlib = L
@@ -184,6 +186,17 @@ class EmRank:
         self.ctx._chk(rc)
         self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
 
+    def estep_bfgs_update(self, indF, alpha):
+        """E-step + F / alpha update sharing one forward pass; returns ind_lkl."""
+        n = self.ctx.n_ind_owned
+        lk = np.empty(n)
+        rc = self.H.nfh_host_estep_bfgs_update(self.ctx.h, n, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
+                                               int(self.indF_fixed), int(self.alpha_fixed), lk.ctypes.data_as(_dp),
+                                               self.stats.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self.ctx._chk(rc)
+        self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
+        return lk
+
     def iteration(self, indF, alpha, want_freq=True):
         """One EM iteration; indF/alpha (float64, n_ind_owned) are updated in place.
         Returns (ind_lkl, freq_of_this_rank's_sites or None); the frequency array is one page-locked
@@ -202,10 +215,12 @@ class EmRank:
             self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
             return lk, fr
         ctx.set_ind_params(indF, alpha)
-        lk = ctx.estep()
-        if self.freq_est and not self.direct:
+        if self.direct or not self.freq_est:
+            lk = self.estep_bfgs_update(indF, alpha)     # posterior tiles go to their owners from the kernel
+        else:
+            lk = ctx.estep()
             self.exchange_posteriors_begin()             # overlaps the host/device BFGS rounds below
-        self.bfgs_update(indF, alpha)
+            self.bfgs_update(indF, alpha)
         fr = None
         if self.freq_est:
             if self.direct:

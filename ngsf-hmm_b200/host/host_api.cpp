@@ -28,6 +28,18 @@ int nfh_host_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
   return rc;
 }
 
+int nfh_host_estep_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed,
+                               int alpha_fixed, double *ind_lkl_out, uint64_t stats_out[3]) {
+  std::vector<double> lkl_tmp;
+  if (!ind_lkl_out) { lkl_tmp.resize(n_ind); ind_lkl_out = lkl_tmp.data(); }
+  BfgsStats st;
+  int rc = bfgs_update_lockstep(ctx, n_ind, indF, alpha, F_fixed != 0, alpha_fixed != 0, &st, ind_lkl_out);
+  if (stats_out) {
+    stats_out[0] = st.rounds; stats_out[1] = st.evaluations; stats_out[2] = st.max_rounds_one_individual;
+  }
+  return rc;
+}
+
 int nfh_host_em_iteration(nfh_ctx *ctx, double *indF, double *alpha, int F_fixed, int alpha_fixed, int freq_est,
                           double *ind_lkl_out, double *freq_out, uint64_t stats_out[3]) {
   const uint64_t n = nfh_n_ind_owned(ctx);
@@ -35,13 +47,7 @@ int nfh_host_em_iteration(nfh_ctx *ctx, double *indF, double *alpha, int F_fixed
   if (rc != NFH_OK) return rc;
   // E-step (EM.cpp:151-185) and F / alpha update (EM.cpp:188-205, old emissions): the optimiser starts at the
   // E-step's parameters, so its first batched round and the E-step share one forward pass
-  std::vector<double> lkl_tmp;
-  if (!ind_lkl_out) { lkl_tmp.resize(n); ind_lkl_out = lkl_tmp.data(); }
-  BfgsStats st;
-  rc = bfgs_update_lockstep(ctx, n, indF, alpha, F_fixed != 0, alpha_fixed != 0, &st, ind_lkl_out);
-  if (stats_out) {
-    stats_out[0] = st.rounds; stats_out[1] = st.evaluations; stats_out[2] = st.max_rounds_one_individual;
-  }
+  rc = nfh_host_estep_bfgs_update(ctx, n, indF, alpha, F_fixed, alpha_fixed, ind_lkl_out, stats_out);
   if (rc != NFH_OK) return rc;
   if (freq_est != 0) rc = nfh_freq_update(ctx, 1, 0, freq_out);  // EM.cpp:224-271 (new posterior)
   return rc;
