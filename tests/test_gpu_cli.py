@@ -159,3 +159,17 @@ def test_replicates_share_one_ingest_and_keep_the_best(tmp_path):
     assert f"Best replicate: {best + 1} (seed {20 + best})" in out
     for ext in ("indF", "ibd", "geno"):
         assert open(tmp_path / f"reps.{ext}", "rb").read() == open(tmp_path / f"single{best}.{ext}", "rb").read()
+
+
+@pytest.mark.parametrize("flag", ["--alpha_fixed", "--indF_fixed"])
+def test_one_parameter_fixed(tmp_path, flag):
+    """Only F or only alpha is optimised: three-point gradient rounds, the other bound collapsed (EM.cpp:427-434)."""
+    N, S = 6, 2500
+    d = sim.simulate(N, S, seed=808, freq=(0.1, 0.5), indF=(0.1, 0.6), alpha=0.02, depth=3.0)
+    sim.write_binary_gl(str(tmp_path / "in.glf"), d.log_gl)
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    common = ["--geno", "in.glf", "--loglkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "0.2",
+              "--indF", "0.2,0.05", flag, "--min_iters", "3", "--max_iters", "4", "--verbose", "0"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    _run(OURS, common + ["--out", "ours"], str(tmp_path))
+    _compare(tmp_path, N, S, f_tol=5e-5)
