@@ -553,13 +553,11 @@ lkl_finish(const TileProd *__restrict__ tile_prod, const LklGroup *__restrict__ 
 // host-side launchers
 // ---------------------------------------------------------------------------
 
-static bool g_attr_done = false;
+// per launch: the attribute belongs to the current device, and a process may drive several
 static void set_smem_attrs() {
-  if (g_attr_done) return;
   cudaFuncSetAttribute(estep_chunk_products, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem));
   cudaFuncSetAttribute(estep_chunk_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TileSmem));
   cudaFuncSetAttribute(lkl_tile_products, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LklSmem));
-  g_attr_done = true;
 }
 
 void launch_estep(const EstepArgs &a, cudaStream_t st) {

@@ -895,12 +895,9 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   const size_t smem_cap = (size_t) 228 * 1024 / freq_occupancy(K) - 1024 - 256;
   const size_t bufs = 2 * FreqTile<G>::tile_bytes(a.n_ind) + FreqTile<G>::kAlign;   // + alignment slack
   const bool want = a.use_maps && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_warp<G, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
-    cudaFuncSetAttribute(freq_emission_warp<G, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
-    attr_done = true;
-  }
+  // per launch: the attribute belongs to the current device, and a process may drive several
+  cudaFuncSetAttribute(freq_emission_warp<G, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
+  cudaFuncSetAttribute(freq_emission_warp<G, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
   if (want && acc + bufs <= smem_cap) freq_emission_warp<G, K, 1><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
   else if (want && a.acc_scratch && bufs <= smem_cap) freq_emission_warp<G, K, 2><<<grid, kFreqThreads, bufs, st>>>(a, tiles);
   else freq_emission_warp<G, K, 0><<<grid, kFreqThreads, acc, st>>>(a, tiles);
@@ -962,11 +959,8 @@ static void launch_team_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   constexpr int kTeams = (kThreads / 32) / W;
   const unsigned tiles = (unsigned) ((a.sites_owned + kTeams - 1) / kTeams);
   size_t smem = (size_t) kTeams * a.n_ind_pad * (sizeof(double) + sizeof(int));
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_team<W, K, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  // per launch: the attribute belongs to the current device, and a process may drive several
+  cudaFuncSetAttribute(freq_emission_team<W, K, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   freq_emission_team<W, K, kThreads><<<grid, kThreads, smem, st>>>(a, tiles);
 }
 
@@ -999,11 +993,8 @@ static void launch_hybrid_variant(const FreqArgs &a, unsigned grid, cudaStream_t
   const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t smem = (size_t) KS * 6 * kFreqThreads * sizeof(double);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(freq_emission_hybrid<G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-    attr_done = true;
-  }
+  // per launch: the attribute belongs to the current device, and a process may drive several
+  cudaFuncSetAttribute(freq_emission_hybrid<G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   freq_emission_hybrid<G, KS><<<grid, kFreqThreads, smem, st>>>(a, tiles);
 }
 

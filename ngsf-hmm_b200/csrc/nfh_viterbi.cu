@@ -333,12 +333,9 @@ viterbi_chunk_trace(ViterbiArgs A) {
 }
 
 void launch_viterbi(const ViterbiArgs &a, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(viterbi_chunk_products, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
-    cudaFuncSetAttribute(viterbi_chunk_pointers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
-    attr_done = true;
-  }
+  // per launch: the attribute belongs to the current device, and a process may drive several
+  cudaFuncSetAttribute(viterbi_chunk_products, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
+  cudaFuncSetAttribute(viterbi_chunk_pointers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(VitSmem));
   dim3 grid(a.n_tiles, (unsigned) a.n_rows_valid);
   viterbi_chunk_products<<<grid, kScanThreads, sizeof(VitSmem), st>>>(a);
   viterbi_tile_scores<<<(unsigned) ((a.n_rows_valid + 3) / 4), 128, 0, st>>>(a);
