@@ -19,6 +19,9 @@
 #include <string>
 #include <vector>
 
+#include <atomic>
+
+#include "parallel.hpp"
 #include "run_state.hpp"
 
 namespace nfh_cli {
@@ -160,19 +163,27 @@ void read_genotypes(RunState &st) {
   const uint64_t n_geno = o.lkl ? 3 : 1;
 
   if (o.in_bin) {
+    // blocks of whole sites: one large read, then the reader's normalisation on all host threads
     const size_t row = N * 3 * sizeof(double);
-    for (uint64_t s = 0; s < S; s++) {
-      double *site = st.log_gl.data() + s * N * 3;
-      if ((size_t) gzread(fh, site, (unsigned) row) != row) {
+    const uint64_t block_sites = std::max<uint64_t>(1, ((size_t) 128 << 20) / row);
+    std::atomic<bool> saw_nan(false);
+    for (uint64_t s0 = 0; s0 < S; s0 += block_sites) {
+      const uint64_t ns = std::min(block_sites, S - s0);
+      double *block = st.log_gl.data() + s0 * N * 3;
+      if ((size_t) gzread(fh, block, (unsigned) (ns * row)) != ns * row) {
         if (gzeof(fh)) fatal(fn, "GENO file at premature EOF. Check GENO file and number of sites!");
         fatal(fn, "cannot read binary GENO file. Check GENO file and number of sites!");
       }
-      for (uint64_t i = 0; i < N; i++) {
-        double *g = site + 3 * i;
-        if (!o.loglkl) log_or_floor(g);
-        normalise(g);
-        if (std::isnan(g[0]) || std::isnan(g[1]) || std::isnan(g[2])) fatal(fn, "NaN found! Is the file format correct?");
-      }
+      const bool take_log = !o.loglkl;
+      parallel_for(ns * N, o.host_threads, [&](uint64_t lo, uint64_t hi, unsigned) {
+        for (uint64_t j = lo; j < hi; j++) {
+          double *g = block + 3 * j;
+          if (take_log) log_or_floor(g);
+          normalise(g);
+          if (std::isnan(g[0]) || std::isnan(g[1]) || std::isnan(g[2])) saw_nan = true;
+        }
+      });
+      if (saw_nan) fatal(fn, "NaN found! Is the file format correct?");
     }
   } else {
     std::vector<char> buf(kLineMax);
@@ -218,11 +229,15 @@ void read_genotypes(RunState &st) {
   o.loglkl = true;
 
   // main(): optional genotype calling, then a second normalisation (ngsF-HMM.cpp:99-117)
-  for (uint64_t j = 0; j < S * N; j++) {
-    double *g = st.log_gl.data() + 3 * j;
-    if (o.call_geno) call_genotype(g);
-    normalise(g);
-  }
+  const bool call = o.call_geno;
+  double *all = st.log_gl.data();
+  parallel_for(S * N, o.host_threads, [&](uint64_t lo, uint64_t hi, unsigned) {
+    for (uint64_t j = lo; j < hi; j++) {
+      double *g = all + 3 * j;
+      if (call) call_genotype(g);
+      normalise(g);
+    }
+  });
 }
 
 }  // namespace nfh_cli

@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <algorithm>
+#include <thread>
+
 #include "run_state.hpp"
 
 namespace nfh_cli {
@@ -65,7 +68,7 @@ void parse_options(Options &o, int argc, char **argv) {
       case 'm': o.min_iters = (unsigned) atoi(optarg); break;
       case 'M': o.max_iters = (unsigned) atoi(optarg); break;
       case 'E': o.min_epsilon = atof(optarg); break;
-      case 'x': o.n_threads = (unsigned) atoi(optarg); break;
+      case 'x': o.n_threads = (unsigned) atoi(optarg); o.n_threads_given = true; break;
       case 'V': o.verbose = (unsigned) atoi(optarg); break;
       case 'S': o.seed = (unsigned) atoi(optarg); break;
       case 'D': o.device = atoi(optarg); break;
@@ -105,6 +108,10 @@ void parse_options(Options &o, int argc, char **argv) {
   if (o.min_iters < 1 || o.max_iters < 1 || o.min_iters >= o.max_iters) fatal(fn, "invalid number of iterations!");
   if (o.n_threads < 1) fatal(fn, "invalid number of threads!");
   if (o.n_rep < 1) fatal(fn, "invalid number of replicates!");
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    o.host_threads = o.n_threads_given ? o.n_threads : std::max(1u, std::min(hw ? hw : 1u, 16u));
+  }
   // The haplotype-frequency paths abort in the reference itself (freq[0] = -1 reaches haplo_freq,
   // gen_func.cpp:1030-1031); keep the same message instead of inventing behaviour.
   if (o.freq_est == 2 || o.e_prob == 2) fatal("haplo_freq", "invalid allele frequencies");

@@ -11,6 +11,10 @@
 #include <string>
 #include <vector>
 
+#include <cmath>
+
+#include "format.hpp"
+#include "parallel.hpp"
 #include "run_state.hpp"
 
 namespace nfh_cli {
@@ -40,7 +44,12 @@ void write_outputs(RunState &st) {
     else if (st.indF[i] > 1 - eps) fprintf(fh, "%.5f\tNA\n", (double) 1);
     else fprintf(fh, "%.5f\t%f\n", st.indF[i], st.alpha[i]);
   }
-  for (uint64_t s = 0; s < S; s++) fprintf(fh, "%f\n", st.freq[s]);
+  for (uint64_t s = 0; s < S; s++) {
+    char num[40];
+    const int len = format_unit_f(st.freq[s], num);
+    num[len] = '\n';
+    fwrite(num, 1, (size_t) len + 1, fh);
+  }
   fclose(fh);
 
   fh = open_out(o.out + ".ibd", "cannot open IBD output file!");
@@ -54,11 +63,30 @@ void write_outputs(RunState &st) {
     line[S] = '\n';
     if (fwrite(line.data(), 1, S + 1, fh) != S + 1) fatal("print_iter", "cannot write PATH info to file!");
   }
-  for (uint64_t i = 0; i < N; i++) {
-    const double *m = st.marg1.data() + i * S;
-    fprintf(fh, "%f", m[0]);
-    for (uint64_t s = 1; s < S; s++) fprintf(fh, "\t%f", m[s]);
-    fputc('\n', fh);
+  // posterior lines: formatted by all host threads, a batch of rows at a time, written in order
+  {
+    const unsigned T = std::max(1u, o.host_threads);
+    std::vector<std::vector<char>> rows(T);
+    std::vector<size_t> used(T, 0);
+    for (uint64_t i0 = 0; i0 < N; i0 += T) {
+      const uint64_t nb = std::min<uint64_t>(T, N - i0);
+      parallel_for(nb, T, [&](uint64_t lo, uint64_t hi, unsigned) {
+        for (uint64_t b = lo; b < hi; b++) {
+          std::vector<char> &buf = rows[b];
+          buf.resize(S * 33 + 2);                       // worst case: every value through snprintf
+          const double *m = st.marg1.data() + (i0 + b) * S;
+          char *w = buf.data();
+          for (uint64_t s = 0; s < S; s++) {
+            if (s) *w++ = '\t';
+            w += format_unit_f(m[s], w);
+          }
+          *w++ = '\n';
+          used[b] = (size_t) (w - buf.data());
+        }
+      });
+      for (uint64_t b = 0; b < nb; b++)
+        if (fwrite(rows[b].data(), 1, used[b], fh) != used[b]) fatal("print_iter", "cannot write IBD output file!");
+    }
   }
   fclose(fh);
 

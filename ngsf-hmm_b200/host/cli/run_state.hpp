@@ -20,6 +20,8 @@ struct Options {   // one field per command-line flag of the reference (parse_ar
   uint64_t n_ind = 0, n_sites = 0;
   int freq_est = 1, e_prob = 1;
   unsigned log = 0, min_iters = 10, max_iters = 100, n_threads = 1, verbose = 1, seed = 0;
+  bool n_threads_given = false;
+  unsigned host_threads = 1;   // threads for parsing / formatting: --n_threads when given, else the host's cores (<= 16)
   double min_epsilon = 1e-5;
   bool have_geno = false, have_pos = false, have_out = false;
   int device = 0;          // --device (extension; not a reference flag)
