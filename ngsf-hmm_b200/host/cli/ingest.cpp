@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
 #include <atomic>
 
 #include "parallel.hpp"
@@ -156,7 +157,8 @@ void read_genotypes(RunState &st) {
   }
   if (o.verbose >= 1) printf("> GENO data\n");
 
-  st.log_gl.assign(S * N * 3, kLogZero);
+  st.log_gl.reset(new double[S * N * 3]);
+  if (!o.in_bin) std::fill(st.log_gl.get(), st.log_gl.get() + S * N * 3, kLogZero);   // skipped lines keep this value
   gzFile fh = gzopen(o.geno.c_str(), o.in_bin ? "rb" : "r");
   if (!fh) fatal(fn, "cannot open GENO file!");
   gzbuffer(fh, 1 << 20);
@@ -169,7 +171,7 @@ void read_genotypes(RunState &st) {
     std::atomic<bool> saw_nan(false);
     for (uint64_t s0 = 0; s0 < S; s0 += block_sites) {
       const uint64_t ns = std::min(block_sites, S - s0);
-      double *block = st.log_gl.data() + s0 * N * 3;
+      double *block = st.log_gl.get() + s0 * N * 3;
       if ((size_t) gzread(fh, block, (unsigned) (ns * row)) != ns * row) {
         if (gzeof(fh)) fatal(fn, "GENO file at premature EOF. Check GENO file and number of sites!");
         fatal(fn, "cannot read binary GENO file. Check GENO file and number of sites!");
@@ -204,7 +206,7 @@ void read_genotypes(RunState &st) {
       }
       if (fields.size() < N * n_geno) fatal(fn, "wrong GENO file format. Less fields than expected!");
       const double *last = fields.data() + (fields.size() - N * n_geno);
-      double *site = st.log_gl.data() + s * N * 3;
+      double *site = st.log_gl.get() + s * N * 3;
       for (uint64_t i = 0; i < N; i++) {
         double *g = site + 3 * i;
         if (o.lkl) {
@@ -230,7 +232,7 @@ void read_genotypes(RunState &st) {
 
   // main(): optional genotype calling, then a second normalisation (ngsF-HMM.cpp:99-117)
   const bool call = o.call_geno;
-  double *all = st.log_gl.data();
+  double *all = st.log_gl.get();
   parallel_for(S * N, o.host_threads, [&](uint64_t lo, uint64_t hi, unsigned) {
     for (uint64_t j = lo; j < hi; j++) {
       double *g = all + 3 * j;

@@ -20,7 +20,7 @@ int main(int argc, char **argv) {
   read_genotypes(st);
   if (st.opt.verbose >= 6) printf("> Init output\n");
   create_device_state(st);
-  std::vector<double>().swap(st.log_gl);   // GL now lives on the device
+  st.log_gl.reset();                       // GL now lives on the device
   if (st.opt.n_rep == 1) {
     init_start_values(st, st.opt.seed);
     run_em(st, true);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include <cmath>
+#include <memory>
 
 #include "format.hpp"
 #include "parallel.hpp"
@@ -92,10 +93,11 @@ void write_outputs(RunState &st) {
 
   // genotype posteriors come from the device (GL lives there): HWE prior with F = Viterbi state
   fh = open_out(o.out + ".geno", "cannot open GENO output file!");
-  std::vector<double> geno(S * N * 3);
+  const size_t n_geno = S * N * 3;
+  std::unique_ptr<double[]> geno(new double[n_geno]);      // no fill pass: the device writes every value
   check(st, nfh_set_freq(st.ctx, st.freq.data()), "nfh_set_freq");
-  check(st, nfh_geno_posterior(st.ctx, st.path.data(), geno.data()), "nfh_geno_posterior");
-  if (fwrite(geno.data(), sizeof(double), geno.size(), fh) != geno.size())
+  check(st, nfh_geno_posterior(st.ctx, st.path.data(), geno.get()), "nfh_geno_posterior");
+  if (fwrite(geno.get(), sizeof(double), n_geno, fh) != n_geno)
     fatal("print_iter", "cannot write GENO output file!");
   fclose(fh);
 }

@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -34,7 +35,8 @@ struct RunState {
   Options opt;
   nfh_ctx *ctx = nullptr;
   std::vector<double> dist_mb;        // n_sites
-  std::vector<double> log_gl;         // site-major n_sites x n_ind x 3, normalised natural-log GL
+  std::unique_ptr<double[]> log_gl;   // site-major n_sites x n_ind x 3, normalised natural-log GL (2.4 GB at
+                                      // configs[1]: allocated without a fill pass)
   std::vector<double> freq, indF, alpha, ind_lkl;
   std::vector<char> path;             // n_ind x n_sites
   std::vector<double> marg1;          // n_ind x n_sites (fetched only for output)

@@ -80,7 +80,7 @@ void create_device_state(RunState &st) {
   Options &o = st.opt;
   check(st, nfh_ctx_create(&st.ctx, o.device, o.n_ind, o.n_sites, 1, 0), "nfh_ctx_create");
   check(st, nfh_upload_pos_dist(st.ctx, st.dist_mb.data()), "nfh_upload_pos_dist");
-  check(st, nfh_upload_gl(st.ctx, st.log_gl.data(), 0, o.n_sites), "nfh_upload_gl");
+  check(st, nfh_upload_gl(st.ctx, st.log_gl.get(), 0, o.n_sites), "nfh_upload_gl");
 }
 
 void init_start_values(RunState &st, unsigned seed) {
