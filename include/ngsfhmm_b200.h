@@ -164,6 +164,22 @@ int nfh_peer_export(nfh_ctx *ctx, int window, unsigned char handle[64]);
 int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char handle[64]);
 int nfh_peer_direct(nfh_ctx *ctx, int enable);
 
+/* The same fused exchange when ONE process drives several contexts (one per GPU, or several on one GPU):
+ * no IPC handle is needed, the peer's receive window is mapped directly.  Enables peer access between the
+ * two devices when they differ.  window = NFH_WIN_POST_RECV or NFH_WIN_EMIS_RECV; peer must be rank
+ * peer_rank of the same geometry. */
+int nfh_peer_set(nfh_ctx *ctx, int window, int peer_rank, nfh_ctx *peer);
+
+/* Block copy between exchange windows of two contexts of one process (the all-to-all of the host plumbing
+ * without a communicator): block src_block of src's window -> block dst_block of dst's window, one block =
+ * [n_ind_local][site_block] doubles.  Queued on src's stream; nfh_sync(src) completes it. */
+int nfh_window_copy_block(nfh_ctx *dst, int dst_window, int dst_block, nfh_ctx *src, int src_window, int src_block);
+
+/* Host access to a window (bytes at byte offset), synchronous: the all-reduce of NFH_WIN_LOGE0_SUM across the
+ * contexts of one process is a read, a host sum and a write. */
+int nfh_window_read(nfh_ctx *ctx, int window, uint64_t offset, uint64_t bytes, void *host_dst);
+int nfh_window_write(nfh_ctx *ctx, int window, uint64_t offset, uint64_t bytes, const void *host_src);
+
 /* Page-lock a caller-owned host array (cudaHostRegister) so that the copies of the calls above move at
  * full PCIe speed instead of being staged: worth it for the arrays that cross every EM iteration
  * (freq_out of nfh_freq_update is 8 bytes per site).  Unregister before freeing the array. */

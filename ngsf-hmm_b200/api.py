@@ -29,6 +29,7 @@ EXPORTS = [
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
     "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister", "nfh_estep_with_batch",
+    "nfh_peer_set", "nfh_window_copy_block", "nfh_window_read", "nfh_window_write",
 ]
 
 
@@ -94,6 +95,10 @@ def load_library():
     L.nfh_peer_export.restype = cint; L.nfh_peer_export.argtypes = [_vp, cint, C.c_char_p]
     L.nfh_peer_import.restype = cint; L.nfh_peer_import.argtypes = [_vp, cint, cint, C.c_char_p]
     L.nfh_peer_direct.restype = cint; L.nfh_peer_direct.argtypes = [_vp, cint]
+    L.nfh_peer_set.restype = cint; L.nfh_peer_set.argtypes = [_vp, cint, cint, _vp]
+    L.nfh_window_copy_block.restype = cint; L.nfh_window_copy_block.argtypes = [_vp, cint, cint, _vp, cint, cint]
+    L.nfh_window_read.restype = cint; L.nfh_window_read.argtypes = [_vp, cint, u64, u64, _vp]
+    L.nfh_window_write.restype = cint; L.nfh_window_write.argtypes = [_vp, cint, u64, u64, _vp]
     L.nfh_sync.restype = cint; L.nfh_sync.argtypes = [_vp]
     L.nfh_stream.restype = _vp; L.nfh_stream.argtypes = [_vp]
     L.nfh_probe_fp64.restype = cint; L.nfh_probe_fp64.argtypes = [_vp, _dp]
@@ -266,6 +271,10 @@ class Context:
 
     def peer_import(self, which, peer_rank, handle):
         self._chk(self.L.nfh_peer_import(self.h, which, peer_rank, handle))
+
+    def peer_set(self, which, peer_rank, peer_ctx):
+        """Same-process fused exchange: map rank peer_rank's receive window directly (no IPC)."""
+        self._chk(self.L.nfh_peer_set(self.h, which, peer_rank, peer_ctx.h))
 
     def peer_direct(self, enable=True):
         self._chk(self.L.nfh_peer_direct(self.h, int(enable)))

@@ -37,6 +37,8 @@ struct nfh_ctx {
   cudaStream_t stream = nullptr;
 
   // recursion side (this rank's individuals, all sites, site-blocked layout)
+  double *dist_t = nullptr;                            // chunk-transposed copy of dist (EstepArgs::dist_t)
+  double *tile_dmax = nullptr, *tile_dsum = nullptr;   // per tile of the distance vector, see nfh_upload_pos_dist
   double *dist = nullptr, *emis_recv = nullptr, *post_send = nullptr, *e0_recv = nullptr;
   double *indF = nullptr, *alpha = nullptr, *ind_lkl = nullptr;
   double4 *chunk_prod = nullptr;
@@ -58,6 +60,7 @@ struct nfh_ctx {
 
   // peer windows (CUDA IPC), see nfh_peer_*
   double *peer_post[kMaxRanks] = {nullptr}, *peer_emis[kMaxRanks] = {nullptr};
+  bool peer_post_ipc[kMaxRanks] = {false}, peer_emis_ipc[kMaxRanks] = {false};   // mapped by cudaIpcOpenMemHandle (to be closed)
   bool peer_direct = false;
 
   int *status = nullptr;
@@ -210,6 +213,9 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   const size_t plane_rec = (size_t) ctx->n_ranks * ctx->n_loc * ctx->site_block * sizeof(double);
   const size_t plane_frq = (size_t) ctx->n_ind_pad * ctx->site_block * sizeof(double);   // same number
   NFH_TRY(alloc((void **) &ctx->dist, ctx->n_sites_pad * sizeof(double), true));
+  NFH_TRY(alloc((void **) &ctx->dist_t, (size_t) ctx->n_tiles * kTile * sizeof(double), true));
+  NFH_TRY(alloc((void **) &ctx->tile_dmax, ctx->n_tiles * sizeof(double), true));
+  NFH_TRY(alloc((void **) &ctx->tile_dsum, ctx->n_tiles * sizeof(double), true));
   // emission-ratio windows start as 1.0 everywhere and the kernels only ever write real sites, so the
   // padding of the last tile stays the identity of the recursions (r = 1 with d = 0)
   NFH_TRY(alloc((void **) &ctx->emis_recv, plane_rec, false));
@@ -263,15 +269,15 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void *dev[] = {ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
+  void *dev[] = {ctx->dist_t, ctx->tile_dmax, ctx->tile_dsum, ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
                  ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
                  ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
                  ctx->status, ctx->freq_passes, ctx->freq_acc, ctx->d_stage};
   for (void *p : dev) if (p) cudaFree(p);
   for (int r = 0; r < kMaxRanks; r++) {
     if (r == ctx->rank) continue;
-    if (ctx->peer_post[r]) cudaIpcCloseMemHandle(ctx->peer_post[r]);
-    if (ctx->peer_emis[r]) cudaIpcCloseMemHandle(ctx->peer_emis[r]);
+    if (ctx->peer_post[r] && ctx->peer_post_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_post[r]);
+    if (ctx->peer_emis[r] && ctx->peer_emis_ipc[r]) cudaIpcCloseMemHandle(ctx->peer_emis[r]);
   }
   if (ctx->n_ranks > 1) {
     if (ctx->post_recv) cudaFree(ctx->post_recv);
@@ -331,6 +337,27 @@ int nfh_upload_pos_dist(nfh_ctx *ctx, const double *dist_mb) {
   if (!dist_mb) return fail(ctx, NFH_ERR_ARG, "nfh_upload_pos_dist: null");
   NFH_CUDA(cudaSetDevice(ctx->device));
   NFH_CUDA(cudaMemcpyAsync(ctx->dist, dist_mb, ctx->n_sites * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // per tile: the largest distance (NaN poisons it, +inf stays +inf) and the sum, which pick the kappa
+  // tier of every (individual, tile) and give the tile's scalar transition factor without a per-site sum
+  std::vector<double> tmax(ctx->n_tiles), tsum(ctx->n_tiles), dt((size_t) ctx->n_tiles * kTile, 0.0);
+  for (uint32_t t = 0; t < ctx->n_tiles; t++) {
+    const uint64_t lo = (uint64_t) t * kTile, hi = std::min(ctx->n_sites, lo + kTile);
+    double mx = 0.0, sum = 0.0;
+    bool nan = false;
+    for (uint64_t s = lo; s < hi; s++) {
+      const double d = dist_mb[s];
+      nan |= d != d;
+      mx = d > mx ? d : mx;
+      sum += d;
+      const uint64_t k = s - lo;                       // site k = 33 thread + j of the tile
+      dt[lo + (k % kChunk) * kScanThreads + k / kChunk] = d;
+    }
+    tmax[t] = nan ? std::nan("") : mx;
+    tsum[t] = sum;
+  }
+  NFH_CUDA(cudaMemcpyAsync(ctx->dist_t, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NFH_CUDA(cudaMemcpyAsync(ctx->tile_dmax, tmax.data(), ctx->n_tiles * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NFH_CUDA(cudaMemcpyAsync(ctx->tile_dsum, tsum.data(), ctx->n_tiles * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   NFH_CUDA(cudaStreamSynchronize(ctx->stream));
   return NFH_OK;
 }
@@ -422,6 +449,7 @@ int nfh_freq_update(nfh_ctx *ctx, int method, int posterior_is_zero, double *fre
 static EstepArgs estep_args(nfh_ctx *ctx) {
   EstepArgs a;
   a.emis = ctx->emis_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
+  a.dist_t = ctx->dist_t; a.tile_dmax = ctx->tile_dmax; a.tile_dsum = ctx->tile_dsum;
   a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
   a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
   a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
@@ -430,6 +458,7 @@ static EstepArgs estep_args(nfh_ctx *ctx) {
   for (int r = 0; r < kMaxRanks; r++) a.post_peers.base[r] = ctx->peer_post[r];
   a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
   a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
+  a.sm_count = ctx->sm_count;
   return a;
 }
 
@@ -502,6 +531,7 @@ static int lkl_batch_impl(nfh_ctx *ctx, uint64_t n_req, const int32_t *ind, cons
                            ctx->stream));
   LklArgs a;
   a.emis = ctx->emis_recv; a.dist = ctx->dist; a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
+  a.tile_dmax = ctx->tile_dmax; a.tile_dsum = ctx->tile_dsum;
   a.groups = ctx->groups; a.tile_prod = ctx->lkl_tile_prod; a.neg_lkl = ctx->neg_lkl;
   a.n_rows = ctx->n_loc; a.n_sites = ctx->n_sites; a.site_block = ctx->site_block;
   a.n_tiles = ctx->n_tiles; a.n_groups = n_groups;
@@ -591,7 +621,9 @@ int nfh_get_posterior(nfh_ctx *ctx, double *marg1_out) {
     const uint64_t s0 = (uint64_t) b * ctx->site_block;
     if (s0 >= ctx->n_sites) break;
     const uint64_t w = std::min(ctx->site_block, ctx->n_sites - s0);
-    const double *src = ctx->post_send + (size_t) b * ctx->n_loc * ctx->site_block;
+    // fused exchange: the E-step stored block b straight into rank b's frequency-side window (source block = me)
+    const double *src = ctx->peer_direct ? ctx->peer_post[b] + (size_t) ctx->rank * ctx->n_loc * ctx->site_block
+                                         : ctx->post_send + (size_t) b * ctx->n_loc * ctx->site_block;
     NFH_CUDA(cudaMemcpy2DAsync(marg1_out + s0, ctx->n_sites * sizeof(double), src, ctx->site_block * sizeof(double),
                                w * sizeof(double), ctx->n_owned, cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -620,20 +652,26 @@ int nfh_geno_posterior(nfh_ctx *ctx, const char *path_all, double *geno_out) {
   return NFH_OK;
 }
 
-int nfh_exchange_window(nfh_ctx *ctx, int window, void **dev_ptr, uint64_t *bytes, uint64_t *bytes_per_peer) {
+static double *window_base(nfh_ctx *ctx, int window, uint64_t *bytes) {
   const uint64_t plane = ctx->n_ind_pad * ctx->site_block * sizeof(double);
-  void *p = nullptr;
-  uint64_t b = plane;
+  *bytes = plane;
   switch (window) {
-    case NFH_WIN_POST_SEND: p = ctx->post_send; break;
-    case NFH_WIN_POST_RECV: p = ctx->post_recv; break;
-    case NFH_WIN_EMIS_SEND: p = ctx->emis_send; break;
-    case NFH_WIN_EMIS_RECV: p = ctx->emis_recv; break;
-    case NFH_WIN_E0_SEND: p = ctx->e0_send; break;
-    case NFH_WIN_E0_RECV: p = ctx->e0_recv; break;
-    case NFH_WIN_LOGE0_SUM: p = ctx->loge0_sum; b = ctx->n_ind_pad * sizeof(double); break;
-    default: return fail(ctx, NFH_ERR_ARG, "nfh_exchange_window: unknown window");
+    case NFH_WIN_POST_SEND: return ctx->post_send;
+    case NFH_WIN_POST_RECV: return ctx->post_recv;
+    case NFH_WIN_EMIS_SEND: return ctx->emis_send;
+    case NFH_WIN_EMIS_RECV: return ctx->emis_recv;
+    case NFH_WIN_E0_SEND: return ctx->e0_send;
+    case NFH_WIN_E0_RECV: return ctx->e0_recv;
+    case NFH_WIN_LOGE0_SUM: *bytes = ctx->n_ind_pad * sizeof(double); return ctx->loge0_sum;
+    default: return nullptr;
   }
+}
+
+int nfh_exchange_window(nfh_ctx *ctx, int window, void **dev_ptr, uint64_t *bytes, uint64_t *bytes_per_peer) {
+  if (window < NFH_WIN_POST_SEND || window > NFH_WIN_LOGE0_SUM)
+    return fail(ctx, NFH_ERR_ARG, "nfh_exchange_window: unknown window");
+  uint64_t b = 0;
+  void *p = window_base(ctx, window, &b);
   if (dev_ptr) *dev_ptr = p;
   if (bytes) *bytes = b;
   if (bytes_per_peer) *bytes_per_peer = b / ctx->n_ranks;
@@ -666,6 +704,61 @@ int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char
   void *p = nullptr;
   NFH_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   slot[peer_rank] = (double *) p;
+  (window == NFH_WIN_POST_RECV ? ctx->peer_post_ipc : ctx->peer_emis_ipc)[peer_rank] = true;
+  return NFH_OK;
+}
+
+int nfh_peer_set(nfh_ctx *ctx, int window, int peer_rank, nfh_ctx *peer) {
+  if (!peer || peer_rank < 0 || peer_rank >= ctx->n_ranks || ctx->n_ranks > kMaxRanks || peer->rank != peer_rank ||
+      peer->n_ranks != ctx->n_ranks || peer->n_ind_total != ctx->n_ind_total || peer->n_sites != ctx->n_sites)
+    return fail(ctx, NFH_ERR_ARG, "nfh_peer_set: peer is not that rank of the same geometry");
+  double **slot = window == NFH_WIN_POST_RECV ? ctx->peer_post : window == NFH_WIN_EMIS_RECV ? ctx->peer_emis : nullptr;
+  if (!slot) return fail(ctx, NFH_ERR_ARG, "nfh_peer_set: only POST_RECV and EMIS_RECV can be mapped");
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  if (peer->device != ctx->device) {
+    int can = 0;
+    NFH_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    if (!can) return fail(ctx, NFH_ERR_ARG, "nfh_peer_set: the two devices have no peer access");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) NFH_CUDA(e);
+    cudaGetLastError();
+  }
+  slot[peer_rank] = window == NFH_WIN_POST_RECV ? peer->post_recv : peer->emis_recv;
+  return NFH_OK;
+}
+
+int nfh_window_copy_block(nfh_ctx *dst, int dst_window, int dst_block, nfh_ctx *src, int src_window, int src_block) {
+  nfh_ctx *ctx = src;
+  uint64_t db = 0, sb = 0;
+  double *d = window_base(dst, dst_window, &db), *s = window_base(src, src_window, &sb);
+  if (!d || !s || dst_window == NFH_WIN_LOGE0_SUM || src_window == NFH_WIN_LOGE0_SUM || db != sb ||
+      dst->n_ranks != src->n_ranks || dst_block < 0 || dst_block >= dst->n_ranks || src_block < 0 ||
+      src_block >= src->n_ranks)
+    return fail(ctx, NFH_ERR_ARG, "nfh_window_copy_block: windows do not match");
+  const uint64_t block = sb / src->n_ranks;
+  NFH_CUDA(cudaSetDevice(src->device));
+  NFH_CUDA(cudaMemcpyPeerAsync((char *) d + (uint64_t) dst_block * block, dst->device,
+                               (const char *) s + (uint64_t) src_block * block, src->device, block, src->stream));
+  return NFH_OK;
+}
+
+int nfh_window_read(nfh_ctx *ctx, int window, uint64_t offset, uint64_t bytes, void *host_dst) {
+  uint64_t wb = 0;
+  const char *p = (const char *) window_base(ctx, window, &wb);
+  if (!p || !host_dst || offset + bytes > wb) return fail(ctx, NFH_ERR_ARG, "nfh_window_read: outside the window");
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  NFH_CUDA(cudaMemcpyAsync(host_dst, p + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NFH_CUDA(cudaStreamSynchronize(ctx->stream));
+  return NFH_OK;
+}
+
+int nfh_window_write(nfh_ctx *ctx, int window, uint64_t offset, uint64_t bytes, const void *host_src) {
+  uint64_t wb = 0;
+  char *p = (char *) window_base(ctx, window, &wb);
+  if (!p || !host_src || offset + bytes > wb) return fail(ctx, NFH_ERR_ARG, "nfh_window_write: outside the window");
+  NFH_CUDA(cudaSetDevice(ctx->device));
+  NFH_CUDA(cudaMemcpyAsync(p + offset, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  NFH_CUDA(cudaStreamSynchronize(ctx->stream));
   return NFH_OK;
 }
 

@@ -74,6 +74,28 @@ __device__ __forceinline__ int renorm2(double &x, double &y) {
   return e;
 }
 
+// The same two renormalisations with the largest entry found on the INTEGER pipe: for non-negative
+// doubles the high words order like the values, so an IMNMX on them replaces the DSETP + selects of
+// fmax() (the FP64 pipe is the bottleneck of every recursion kernel).  NaN entries have the largest
+// high word and leave the scale untouched, as in renorm().
+__device__ __forceinline__ int exponent_of_hi(int hi) {
+  const int be = (hi >> 20) & 0x7ff;
+  return (be == 0 || be == 0x7ff) ? 0 : max(-1000, min(1000, be - 1023));
+}
+__device__ __forceinline__ int renorm_i(M2 &m) {
+  const int e = exponent_of_hi(max(max(__double2hiint(m.a), __double2hiint(m.b)),
+                                   max(__double2hiint(m.c), __double2hiint(m.d))));
+  const double s = pow2i(-e);
+  m.a *= s; m.b *= s; m.c *= s; m.d *= s;
+  return e;
+}
+__device__ __forceinline__ int renorm2_i(double &x, double &y) {
+  const int e = exponent_of_hi(max(__double2hiint(x), __double2hiint(y)));
+  const double s = pow2i(-e);
+  x *= s; y *= s;
+  return e;
+}
+
 // ---------------------------------------------------------------------------
 // Factored site matrix.  With c = exp(-alpha d) and kappa = (1-c)/c = e^{alpha d} - 1
 //   T_s = c I + (1-c) 1 q'  =  c [ I + kappa 1 q' ]
@@ -90,6 +112,33 @@ __device__ __forceinline__ int renorm2(double &x, double &y) {
 // below half an ulp.  Growth is bounded by renormalising at least every 6 sites (2^660).
 // ---------------------------------------------------------------------------
 constexpr double kBigX = 76.24618986159398;           // 110 ln 2: largest exponent of the factored form
+
+// Three evaluation tiers of kappa, chosen per (individual, tile) from alpha * (largest distance of the
+// tile), so the choice is uniform over the CTA:
+//   kTierFast  x < 0.0054 (< ln2/128) everywhere: expm1_pos() reduces to its polynomial (k = 0, table
+//              entry 1), so expm1_small() returns the SAME BITS with 5 instead of 11 FP64 instructions;
+//   kTierMid   x <= 1 everywhere: expm1_pos() without the clamp;
+//   kTierSlow  anything else (chromosome starts d = +inf, NaN, large alpha d): clamp at kBigX.
+// In the first two tiers nothing is clamped, so the scalar part of the tile's transition product,
+// sum_s -alpha d_s, is -alpha * (sum of the tile's distances), a per-tile constant precomputed at upload.
+enum : int { kTierFast = 0, kTierMid = 1, kTierSlow = 2 };
+constexpr double kFastX = 0.0054;
+constexpr double kMidX = 1.0;
+__device__ __forceinline__ int kappa_tier(double alpha_max, double tile_dmax) {
+  const double x = alpha_max * tile_dmax;               // NaN compares false twice -> slow tier
+  return x < kFastX ? kTierFast : (x <= kMidX ? kTierMid : kTierSlow);
+}
+// sites between two renormalisations: growth per site is at most (1 + kappa) * max(1, r), r = e1/e0 <= 2^50
+template <int TIER> struct TierTraits { static constexpr int kWindow = TIER == kTierSlow ? 4 : 8; };
+
+template <int TIER>
+__device__ __forceinline__ double tier_kappa(double x, const double *__restrict__ tab, double &log_scale) {
+  if (TIER == kTierFast) return expm1_small(x);
+  if (TIER == kTierMid) return expm1_pos(x, tab);
+  const double xc = fmin(x, kBigX);
+  log_scale -= xc;
+  return expm1_pos(xc, tab);
+}
 
 // kappa for x = alpha * d; adds log c = -x (natural log) to log_scale.
 __device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab, double &log_scale) {

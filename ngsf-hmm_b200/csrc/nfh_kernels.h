@@ -38,6 +38,8 @@ struct LklGroup {   // objective requests of one individual sharing one read of 
 struct EstepArgs {
   const double *emis;        // emission ratio, blocked [n_ranks][n_rows][site_block]
   const double *dist;        // [n_ranks * site_block] Mb
+  const double *dist_t;      // the same distances, chunk-transposed per tile: site 33 t + j of tile T at T*4224 + j*128 + t
+  const double *tile_dmax, *tile_dsum;   // per tile: largest distance and sum of distances (kappa tiers, nfh_device.cuh)
   const double *indF, *alpha;
   const double *loge0_sum;   // [n_rows] sum over sites of log e0
   double4 *chunk_prod;       // [n_rows][n_tiles * 128] direction-only chunk products
@@ -49,10 +51,12 @@ struct EstepArgs {
   int *status;
   uint64_t n_rows, n_rows_valid, n_sites, site_block;
   uint32_t n_tiles;
+  int sm_count;
 };
 
 struct LklArgs {
   const double *emis, *dist, *loge0_sum;
+  const double *tile_dmax, *tile_dsum;
   const LklGroup *groups;
   TileProd *tile_prod;       // [n_groups][kMaxPoints][n_tiles]
   double *neg_lkl;

@@ -15,9 +15,10 @@
 namespace nfh {
 
 // 2^(j/64), j = 0..63, round-to-nearest doubles; copied to shared memory by
-// every CTA that calls expm1_pos() (per-lane indices would serialise in the
-// constant cache).
-__constant__ double kExp2Table[64] = {
+// every CTA that calls expm1_pos().  Kept in global memory: the copy is one
+// coalesced load per thread, whereas per-lane indices into the constant bank
+// would serialise in the constant cache (and so would the lookups themselves).
+__device__ const double kExp2Table[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572,
     1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924,
     1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
@@ -57,6 +58,16 @@ __device__ __forceinline__ double expm1_pos(double x, const double *__restrict__
   const double t = tab[ki & 63];
   const double ts = __hiloint2double(__double2hiint(t) + ((ki >> 6) << 20), __double2loint(t));   // T 2^(k>>6)
   return fma(ts, p, ts - 1.0);
+}
+
+// kappa = e^x - 1 for 0 <= x < 0.0054: the polynomial of expm1_pos() alone.  For such x expm1_pos() has
+// k = 0, r = x, table entry 1.0 and returns fma(1, p, 0) = p, so the two functions agree bit for bit.
+__device__ __forceinline__ double expm1_small(double x) {
+  double p = fma(x, 1.0 / 120.0, 1.0 / 24.0);
+  p = fma(p, x, 1.0 / 6.0);
+  p = fma(p, x, 0.5);
+  p = p * x;
+  return fma(p, x, x);
 }
 
 // 1/x for normal positive x: hardware seed (~2^-23) + one cubic Newton step

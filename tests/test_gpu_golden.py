@@ -75,28 +75,40 @@ def test_full_em_matches_reference_fixture():
 
 def test_full_em_config1_shape_with_adjudication():
     """BASELINE configs[0] shape: 20 individuals x 10,000 sites, --freq_est 1, --freq 0.1 --indF 0.1,0.2,
-    full EM to convergence.  The reference's finite-difference BFGS amplifies the rounding noise of its own
-    log-space forward() ~1e5x, so 3 of its 20 F values move by 1e-5..3.5e-5 when the SAME EM is run with
-    an extended-precision objective (tests/golden/make_golden_extended.py).  Per individual we must match
-    the reference OR that extended-precision run to 1e-6 ("chaotic parity")."""
+    full EM to convergence, against the unmodified reference ("chaotic parity").
+
+    alpha and the site frequencies must match the reference to 1e-6 outright.  F: the reference's
+    finite-difference BFGS amplifies the rounding noise of its own log-space forward() ~1e5x, and 4 of its
+    20 F values move by 1e-6..3.5e-5 when the SAME EM is run with an extended-precision objective
+    (tests/golden/make_golden_extended.py; the log-space rerun reproduces the reference bit for bit).
+    So at least 16 of 20 must sit within 1e-6 of the reference; every exception must sit within 1e-6 of
+    the extended-precision run AND reach at least the reference's likelihood, both evaluated in long
+    double on the same emissions: lkl(F, alpha) >= lkl(F_ref, alpha_ref) - 1e-9 |lkl|."""
     g = {k: v for k, v in np.load(os.path.join(HERE, "golden", "em_cfg1_adjudication.npz")).items()}
     N, S = int(g["n_ind"]), int(g["n_sites"])
     from _oracle import Oracle
+    orc = Oracle()
     d = sim.simulate(N, S, seed=int(g["seed"]), freq=0.2, indF=0.5, alpha=0.01, depth=2.0)
-    gl = Oracle().normalize_gl(np.transpose(d.log_gl, (1, 0, 2)))
+    gl = orc.normalize_gl(np.transpose(d.log_gl, (1, 0, 2)))
     with _ctx_from_gl_norm(gl, d.dist_mb, 0.1, 0.1, 0.2) as ctx:
         runner = nfh.EmRank(ctx, freq_est=1)
         F = np.full(N, 0.1); a = np.full(N, 0.2)
         out = nfh.run_em(runner, F, a, min_iters=10, max_iters=100)
     assert out["iterations"] == int(g["iters_ext"])
     np.testing.assert_allclose(out["tot_lkl"], float(g["tot_ref"]), rtol=1e-9)
+    np.testing.assert_allclose(a, g["a_ref"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out["freq"], g["freq_ref"], rtol=0, atol=1e-6)
     near_ref = np.abs(F - g["F_ref"]) <= 1e-6
     near_ext = np.abs(F - g["F_ext"]) <= 1e-6
-    print(f"F: {near_ref.sum()}/{N} within 1e-6 of the reference, {near_ext.sum()}/{N} of the extended-precision EM")
-    assert (near_ref | near_ext).all(), (F - g["F_ref"], F - g["F_ext"])
-    assert near_ext.sum() >= near_ref.sum()           # we sit with the more precise objective
-    assert ((np.abs(a - g["a_ref"]) <= 1e-6) | (np.abs(a - g["a_ext"]) <= 1e-6)).all()
-    assert ((np.abs(out["freq"] - g["freq_ref"]) <= 1e-6) | (np.abs(out["freq"] - g["freq_ext"]) <= 1e-6)).all()
+    print(f"F: {near_ref.sum()}/{N} within 1e-6 of the reference, {near_ext.sum()}/{N} of the extended-precision EM; "
+          f"max |F - F_ref| = {np.abs(F - g['F_ref']).max():.2e}")
+    assert near_ref.sum() >= 16, (F - g["F_ref"])
+    _, e = orc.freq_emission(gl, None, g["freq_ref"], update_freq=False)
+    for i in np.nonzero(~near_ref)[0]:
+        assert near_ext[i], (i, F[i], g["F_ref"][i], g["F_ext"][i])
+        lk_ours = orc.estep_extended(e[i], d.dist_mb, F[i], a[i])[1]
+        lk_ref = orc.estep_extended(e[i], d.dist_mb, g["F_ref"][i], g["a_ref"][i])[1]
+        assert lk_ours >= lk_ref - 1e-9 * abs(lk_ref), (i, lk_ours, lk_ref)
     p_ref = np.unpackbits(g["path_ref"], axis=1)[:, :S]; p_ext = np.unpackbits(g["path_ext"], axis=1)[:, :S]
     for i in range(N):
         assert (out["path"][i] == p_ref[i]).all() or (out["path"][i] == p_ext[i]).all()

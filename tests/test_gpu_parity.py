@@ -300,10 +300,15 @@ def test_tiny_and_tile_boundary_shapes(oracle, N, S):
         np.testing.assert_allclose(out, want, rtol=LKL_RTOL)
 
 
-def test_full_size_properties_without_oracle():
-    """BASELINE configs[1] width (1,000,000 sites) on a few individuals: properties that need no CPU oracle.
-    forward == backward log-likelihood (checked in-kernel, EM.cpp:166), objective(F, alpha) == -E-step lkl,
-    posterior in [0, 1] with the clamp gaps empty, frequency update idempotent given the same posterior."""
+def test_full_size_properties_and_extended_precision(oracle):
+    """BASELINE configs[1] width (1,000,000 sites) on 4 individuals.
+    (a) Against the long-double restatement of forward/backward/posterior (the adjudicator of SURVEY.md
+        finding 5 - the reference's own log-space recursion is noisier than 1e-8 at this length):
+        log-likelihood 1e-9 relative, posterior 1e-8 absolute except clamp-threshold flips; the
+        reference-arithmetic forward() must also agree to 1e-9 relative.
+    (b) Properties that need no oracle: forward == backward log-likelihood (checked in-kernel, EM.cpp:166),
+        objective(F, alpha) == -E-step lkl, posterior in [0, 1] with the clamp gaps empty, frequency update
+        idempotent given the same posterior, tracts follow the posterior."""
     N, S = 4, 1_000_000
     import torch
     gen = sim.simulate_torch(N, S, device="cuda", seed=5)
@@ -318,6 +323,18 @@ def test_full_size_properties_without_oracle():
         post = ctx.get_posterior()
         assert post.min() >= 0 and post.max() <= 1
         assert not ((post > 0) & (post < 1e-5)).any() and not ((post < 1) & (post > 1 - 1e-5)).any()
+        # (a) the adjudicator, one individual at a time (about a second each)
+        gl_ind = np.ascontiguousarray(np.transpose(gen["log_gl"].numpy(), (1, 0, 2)))
+        _, e = oracle.freq_emission(gl_ind, None, np.full(S, 0.1), update_freq=False)
+        for i in range(N):
+            m_ext, lk_ext = oracle.estep_extended(e[i], gen["dist_mb"], F[i], a[i])
+            assert abs(lk[i] - lk_ext) <= 1e-9 * abs(lk_ext), (i, lk[i], lk_ext)
+            assert abs(lk[i] - oracle.forward(e[i], gen["dist_mb"], F[i], a[i])) <= 1e-9 * abs(lk_ext)
+            clamped = np.where(m_ext < 1e-5, 0.0, np.where(m_ext > 1 - 1e-5, 1.0, m_ext))
+            diff = np.abs(post[i] - clamped)
+            flips = (diff > 1e-8) & ((np.abs(m_ext - 1e-5) < 1e-9) | (np.abs(m_ext - (1 - 1e-5)) < 1e-9))
+            assert ((diff > 1e-8) & ~flips).sum() == 0, (i, diff.max())
+        del gl_ind, e
         f1 = ctx.freq_update(1)
         lk1 = ctx.estep()
         ctx.set_freq(np.full(S, 0.3))                      # the frequency EM ignores its previous value
