@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py - individual-sites per second per EM iteration on B200.
 
-One "step" = one full EM iteration of the hot path on a fixed synthetic input
-(the reference's iter_EM, EM.cpp:139-289): fused forward-backward E-step with
-posteriors, lockstep L-BFGS-B update of every individual's (F, alpha) around
-batched objective launches, per-site allele-frequency EM fused with the
-emission refresh.  Workload at N GPUs: BASELINE.json configs[1] per GPU
-(100 individuals x 1,000,000 sites, depth-2 GLs, --freq_est 1, start values
---freq 0.1 --indF 0.1,0.2) => weak scaling: N*100 individuals.
+One "step" = one EM iteration of the hot path on a fixed synthetic input (the reference's iter_EM,
+EM.cpp:139-289).  Workloads (BASELINE.json configs, weak scaling: the per-GPU work is fixed):
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  --config 1 (default)  configs[1] per GPU: 100 individuals x 1,000,000 sites, --freq_est 1, start values
+                        --freq 0.1 --indF 0.1,0.2: E-step + lockstep L-BFGS-B update of every (F, alpha) around
+                        batched objective launches + per-site allele-frequency EM fused with the emission refresh.
+  --config 2            configs[2] at 8 GPUs: 125 individuals x 10,000,000 sites per GPU, same step.
+  --config 4            configs[4] at 8 GPUs: 1,250 individuals x 1,000,000 sites per GPU, --indF_fixed
+                        --alpha_fixed --freq_est 0: the step is the fixed-parameter iteration (forward-backward +
+                        posterior); the Viterbi tract decoding is timed beside it.
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every
-field is obtained.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|4]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
 """
 from __future__ import annotations
 
@@ -33,15 +35,19 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 METRIC = "ind-sites/sec per EM iteration"
 UNIT = "ind-sites/s"
-IND_PER_GPU = 100
-N_SITES = 1_000_000
+CONFIGS = {   # individuals per GPU, sites, free parameters
+    1: dict(n_ind=100, n_sites=1_000_000, fixed=False, name="configs[1]"),
+    2: dict(n_ind=125, n_sites=10_000_000, fixed=False, name="configs[2]"),
+    4: dict(n_ind=1250, n_sites=1_000_000, fixed=True, name="configs[4]"),
+}
 START_FREQ, START_F, START_ALPHA = 0.1, 0.1, 0.2
 # algorithmic work per unit, stated in DESIGN.md "Measurement"
 ESTEP_BYTES_PER_IND_SITE = 24.0          # read 2 emissions, write 1 posterior
 FREQ_FLOPS_PER_IND_PASS = 13.75          # odds-form est_maf contribution: 8 FP64 instructions (5.75 of them FMA)
 FREQ_INSTR_PER_IND_PASS = 8.0            # -> at most 13.75/16 of the DFMA peak; passes per site are counted by the kernel
 LKL_FLOPS_PER_IND_SITE_POINT = 14.0      # factored 2x2 update: 2 ADD + 4 FMA + 4 MUL per objective point and site
-EXP_FLOPS = 21.0                         # kappa = expm1(alpha d): 13 FP64 instructions, 8 of them FMA; 3 per 5 points
+EXP_FLOPS = 21.0                         # kappa = expm1(alpha d), table tier: 13 FP64 instructions, 8 of them FMA; 3 per 5 points
+FP64_LANES_PER_SM = 64                   # B200: 64 FP64 FMA lanes per SM -> arithmetic peak = SMs x 64 x 2 x clock
 
 
 def parse_args():
@@ -50,11 +56,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n_ind", type=int, default=IND_PER_GPU, help="individuals per GPU")
-    ap.add_argument("--n_sites", type=int, default=N_SITES)
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS))
+    ap.add_argument("--n_ind", type=int, default=None, help="individuals per GPU (default: the config's)")
+    ap.add_argument("--n_sites", type=int, default=None)
     ap.add_argument("--no_cpu_baseline", action="store_true")
-    ap.add_argument("--cpu_sites", type=int, default=4000, help="sites of the bounded CPU-baseline sample")
-    return ap.parse_args()
+    ap.add_argument("--no_parity_check", action="store_true")
+    ap.add_argument("--cpu_sites", type=int, default=20000, help="sites of the bounded CPU sample (reference arm)")
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.n_ind = a.n_ind or cfg["n_ind"]
+    a.n_sites = a.n_sites or cfg["n_sites"]
+    a.fixed = cfg["fixed"]
+    a.cfg_name = cfg["name"]
+    return a
 
 
 # ---------------------------------------------------------------------------
@@ -146,12 +160,13 @@ class ClockSampler:
 
 def ncu_traffic():
     """DRAM bytes per individual-site measured by ncu (committed under profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01f.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh)["bytes_per_ind_site"]
-    except Exception:  # noqa: BLE001
-        return None
+    for name in ("ncu_traffic_r02.json", "ncu_traffic_r01f.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                return json.load(fh)["bytes_per_ind_site"]
+        except Exception:  # noqa: BLE001
+            continue
+    return None
 
 
 def measured_peaks():
@@ -163,20 +178,36 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_text(args, n_total):
+    if args.fixed:
+        flags = "--indF FILE --indF_fixed --alpha_fixed --freq FILE --freq_est 0 (true parameter values)"
+    else:
+        flags = "--freq_est 1, start --freq 0.1 --indF 0.1,0.2"
+    return (f"{args.cfg_name} per GPU: {args.n_ind} individuals x {args.n_sites} sites, depth-2 GL, {flags}; "
+            f"{n_total} individuals total")
+
+
 # ---------------------------------------------------------------------------
 def reference_arm(args, as_cpu_baseline=False):
     """The UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on host cores: one step = one
-    iter_EM() on a bounded sample of the workload (same generator, same start values)."""
+    iter_EM() on a bounded sample of the workload (same generator, same start values, same flags)."""
     from _oracle import Ref
     import ngsf_hmm_b200  # noqa: F401
     from ngsf_hmm_b200 import sim
     cores = os.cpu_count() or 1
-    N, S = args.n_ind, args.cpu_sites
+    N = min(args.n_ind, 100)                    # the reference holds ~250 B per individual-site
+    S = args.cpu_sites
     d = sim.simulate_torch(N, S, device="cpu", seed=1002, site_chunk=1 << 14)
     threads = min(cores, N)
     ref = Ref()
-    st = ref.state(d["log_gl"].numpy(), d["dist_mb"], START_FREQ, START_F, START_ALPHA, freq_est=1, n_threads=threads)
-    steps, warm = (1, 0) if as_cpu_baseline else (args.steps, min(args.warmup, 1))
+    if args.fixed:
+        st = ref.state(d["log_gl"].numpy(), d["dist_mb"], np.clip(d["true_freq"], 0.01, 0.49),
+                       np.clip(d["true_F"], 1e-6, 1 - 1e-6), d["true_alpha"], freq_est=0, n_threads=threads,
+                       indF_fixed=True, alpha_fixed=True)
+    else:
+        st = ref.state(d["log_gl"].numpy(), d["dist_mb"], START_FREQ, START_F, START_ALPHA, freq_est=1,
+                       n_threads=threads)
+    steps, warm = (1, 0) if as_cpu_baseline else (args.steps, args.warmup)
     for _ in range(warm):
         st.iter_EM()
     t0 = time.perf_counter()
@@ -186,20 +217,56 @@ def reference_arm(args, as_cpu_baseline=False):
     st.close()
     value = N * S / dt
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-          "sample": f"{N} individuals x {S} sites of the same synthetic workload, {steps} iter_EM() call(s) of the "
-                    f"unmodified reference in-process (oracle/_ref), --n_threads {threads} of {cores} host cores; "
-                    f"its frequency loop is serial"}
+          "sample": f"{N} individuals x {S} sites of the same synthetic workload, {warm} warm-up + {steps} timed "
+                    f"iter_EM() call(s) of the unmodified reference in-process (oracle/_ref), --n_threads {threads} "
+                    f"of {cores} host cores; its frequency loop is serial.  A per-unit RATE on a sample, not the same "
+                    f"job timed twice"}
     if as_cpu_baseline:
         return cb
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[1] sample: {N} ind x {S} sites, --freq_est 1, --freq 0.1 --indF 0.1,0.2"},
+            "config": {"workload": f"{args.cfg_name} sample: {N} ind x {S} sites, " +
+                                   ("fixed parameters, --freq_est 0" if args.fixed else
+                                    "--freq_est 1, --freq 0.1 --indF 0.1,0.2")},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 # ---------------------------------------------------------------------------
+def upload_synthetic(ctx, sim, dev, n_total, n_sites, seed=1002):
+    """Synthetic GL for this rank's SITE block, all individuals, generated on the GPU chunk by chunk and handed
+    to nfh_upload_gl as device memory (no host copy).  Returns (dist_mb, true_F, true_alpha, true_freq of the
+    block, seconds generating, seconds uploading, bytes)."""
+    import torch
+    chunk = 1 << 18
+    while chunk > 4096 and chunk * n_total > 2.2e8:
+        chunk >>= 1
+    s0, s1 = ctx.site_begin, ctx.site_begin + ctx.sites_owned
+    buf = torch.empty((chunk, n_total, 3), dtype=torch.float64, device=dev)
+    t_gen = t_up = 0.0
+    meta, freq_parts = None, []
+    c0 = (s0 // chunk) * chunk
+    while c0 < s1:
+        lo, hi = max(c0, s0), min(c0 + chunk, s1)
+        t0 = time.perf_counter()
+        gen = sim.simulate_torch(n_total, n_sites, device=dev, seed=seed, site_chunk=chunk, site_begin=lo, site_end=hi,
+                                 out=buf[:hi - lo])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ctx.upload_gl(buf[:hi - lo], first_site=lo)
+        t_gen += t1 - t0; t_up += time.perf_counter() - t1
+        freq_parts.append(gen["true_freq"])
+        meta = gen
+        c0 += chunk
+    if meta is None:                            # a rank without sites still needs the distances
+        meta = sim.simulate_torch(n_total, n_sites, device=dev, seed=seed, site_chunk=chunk, site_begin=0, site_end=0)
+    del buf
+    torch.cuda.empty_cache()
+    freq = np.concatenate(freq_parts) if freq_parts else np.empty(0)
+    return meta["dist_mb"], meta["true_F"], meta["true_alpha"], freq, t_gen, t_up, ctx.sites_owned * n_total * 24
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -213,7 +280,7 @@ def main():
 
     import torch
     import ngsf_hmm_b200 as nfh
-    from ngsf_hmm_b200 import sim
+    from ngsf_hmm_b200 import selfcheck, sim
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
@@ -226,61 +293,73 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_ranks = world
     N_total, S = args.n_ind * n_ranks, args.n_sites
+    direct = world > 1 and os.environ.get("NFH_PEER_DIRECT", "1") != "0"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- setup (untimed): synthetic GL for this rank's SITE block, all individuals -> pinned host -> upload
-    t_setup = time.perf_counter()
-    ctx = nfh.Context(N_total, S, device=local_rank, n_ranks=n_ranks, rank=rank)
-    gen = sim.simulate_torch(N_total, S, device=dev, seed=1002, site_begin=ctx.site_begin,
-                             site_end=ctx.site_begin + ctx.sites_owned)
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t_setup
-    t_up0 = time.perf_counter()
-    ctx.upload_gl(gen["log_gl"])
-    ctx.upload_pos_dist(gen["dist_mb"])
-    t_upload = time.perf_counter() - t_up0
-    gl_bytes = gen["log_gl"].numel() * 8
-    del gen
-    torch.cuda.empty_cache()
+    # ---- multi-rank self-check (untimed): the sharded path against one rank, before anything is timed
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = selfcheck.multi_rank_check(local_rank, direct=direct)
+        flag = torch.tensor([1 if (rank != 0 or parity["ok"]) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "multi-rank parity check failed", "parity_check": parity}), flush=True)
+            dist.destroy_process_group()
+            return 1
 
-    runner = nfh.EmRank(ctx, freq_est=1)
+    # ---- setup (untimed for `value`, counted in e2e_full_run): synthetic GL -> device -> nfh_upload_gl
+    t_run0 = time.perf_counter()
+    ctx = nfh.Context(N_total, S, device=local_rank, n_ranks=n_ranks, rank=rank)
+    dist_mb, true_F, true_alpha, true_freq, t_gen, t_upload, gl_bytes = upload_synthetic(ctx, sim, dev, N_total, S)
+    t0 = time.perf_counter()
+    ctx.upload_pos_dist(dist_mb)
+    t_upload += time.perf_counter() - t0
+
+    freq_est = 0 if args.fixed else 1
+    runner = nfh.EmRank(ctx, freq_est=freq_est, indF_fixed=args.fixed, alpha_fixed=args.fixed)
     exchange = "none (1 rank)"
     if world > 1:
-        if os.environ.get("NFH_PEER_DIRECT", "1") != "0":
+        if direct:
             runner.enable_peer_direct()
             exchange = "fused: kernels store into peer windows over NVLink (CUDA IPC)"
         else:
             exchange = "NCCL all-to-all"
     n_own = ctx.n_ind_owned
+    own = slice(ctx.ind_begin, ctx.ind_begin + n_own)
 
     def reset_state():
-        ctx.set_freq(np.full(ctx.sites_owned, START_FREQ))
-        F = np.full(n_own, START_F); a = np.full(n_own, START_ALPHA)
+        if args.fixed:
+            ctx.set_freq(np.clip(true_freq, 0.01, 0.49))
+            F = np.clip(true_F[own], 1e-6, 1 - 1e-6).copy(); a = true_alpha[own].copy()
+        else:
+            ctx.set_freq(np.full(ctx.sites_owned, START_FREQ))
+            F = np.full(n_own, START_F); a = np.full(n_own, START_ALPHA)
         ctx.set_ind_params(F, a)
         runner.refresh_emissions()
         return F, a
 
-    F, a = reset_state()
-    for _ in range(args.warmup):
-        runner.iteration(F, a, want_freq=True)       # also page-locks the frequency download buffer (one-off)
-
-    # ---- device-timed region: K successive EM iterations, state resident in HBM
-    ctx.timing(True)
-    ctx.timing_read(reset=True)
-    ctx.freq_passes(reset=True)
-    launches0 = ctx.kernel_launches
-    evals0, rounds0 = runner.total_evals, runner.total_rounds
     ext = torch.cuda.ExternalStream(ctx.stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     try:
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
     except Exception:  # noqa: BLE001
         gpu_uuid = None
     sampler = ClockSampler(local_rank, gpu_uuid)
+
+    # ---- device-timed leg: reset, W warm-up iterations, then K EM iterations, state resident in HBM
+    F, a = reset_state()
+    for _ in range(args.warmup):
+        runner.iteration(F, a, want_freq=bool(freq_est))    # also page-locks the frequency download buffer (one-off)
+    ctx.timing(True)
+    ctx.timing_read(reset=True)
+    ctx.freq_passes(reset=True)
+    launches0 = ctx.kernel_launches
+    evals0, rounds0 = runner.total_evals, runner.total_rounds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if rank == 0:
         sampler.start()
@@ -297,39 +376,52 @@ def main():
     launches = ctx.kernel_launches - launches0
     evals, rounds = runner.total_evals - evals0, runner.total_rounds - rounds0
 
-    # ---- end-to-end region: the same K iterations through the host-buffer API, wall clock,
-    #      parameters uploaded and lkl / F / alpha / freq downloaded every step
+    # ---- end-to-end leg: the SAME iterations (reset + the same warm-up first) through the host-buffer API, wall
+    #      clock, parameters uploaded and lkl / F / alpha / freq downloaded every step
+    F, a = reset_state()
+    for _ in range(args.warmup):
+        runner.iteration(F, a, want_freq=bool(freq_est))
     barrier()
     t0 = time.perf_counter()
+    fr = None
     for _ in range(args.steps):
-        lk, fr = runner.iteration(F, a, want_freq=True)
+        lk, fr = runner.iteration(F, a, want_freq=bool(freq_est))
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     h2d = 2 * n_own * 8 + (evals / max(args.steps, 1)) * (4 + 8 + 8)
-    d2h = n_own * 8 + ctx.sites_owned * 8 + (evals / max(args.steps, 1)) * 8
+    d2h = n_own * 8 + (ctx.sites_owned * 8 if freq_est else 0) + (evals / max(args.steps, 1)) * 8
 
-    # ---- the E-step on its own (products + carries + apply): inside an EM iteration its forward products
-    #      ride on the first objective round, so the per-step "estep" time covers carries + apply only
+    # ---- the E-step on its own (products + carries + apply): inside a free-parameter EM iteration its forward
+    #      products ride on the first objective round, so the per-step "estep" time covers carries + apply only
     ctx.timing(True)
     ctx.timing_read(reset=True)
     for _ in range(5):
-        ctx.estep()
+        ctx.estep_async()
+    ctx.sync()
     estep_alone_ms = ctx.timing_read(reset=True)["estep"][0] / 5.0
-    ctx.timing(False)
 
-    # ---- one-off costs of a whole run, reported beside the per-iteration numbers
+    # ---- end of a run: emission refresh with e0, Viterbi decoding, downloads (one-off per run)
     t1 = time.perf_counter()
     runner.refresh_emissions(with_e0=True)
+    ctx.set_ind_params(F, a)
+    ctx.sync()
+    t2 = time.perf_counter()
     path = ctx.viterbi()
+    t3 = time.perf_counter()
+    vit = ctx.timing_read(reset=True)
+    ctx.timing(False)
     post = ctx.get_posterior()
-    t_final = time.perf_counter() - t1
-    fp64_peak = ctx.probe_fp64()
+    t4 = time.perf_counter()
+    t_full = t4 - t_run0
+    fp64_probe = ctx.probe_fp64()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, estep_alone_ms, (t4 - t1) * 1e3, vit["viterbi"][0]], dtype=torch.float64,
+                         device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(times[0]), float(times[1])
+    dev_ms, e2e_ms, estep_alone_ms, t_final_ms, vit_ms = (float(x) for x in times)
 
     if rank == 0:
         units = float(N_total) * S * args.steps
@@ -339,57 +431,84 @@ def main():
         rank_units = float(n_own) * S                       # recursion-side units of this rank per step
         freq_units = float(N_total) * ctx.sites_owned       # frequency-side units of this rank per step
         estep_gbs = ESTEP_BYTES_PER_IND_SITE * rank_units / (estep_alone_ms * 1e-3) / 1e9
-        passes_per_site = site_passes / max(ctx.sites_owned * args.steps, 1)
-        freq_tf = FREQ_FLOPS_PER_IND_PASS * passes_per_site * freq_units / (per_step["freq"] * 1e-3) / 1e12
-        evals_step = evals / args.steps
-        lkl_flops = (LKL_FLOPS_PER_IND_SITE_POINT + 0.6 * EXP_FLOPS) * evals_step * S
-        lkl_tf = lkl_flops / (per_step["lkl_batch"] * 1e-3) / 1e12 if per_step["lkl_batch"] > 0 else 0.0
-        dominant = max(("estep", "lkl_batch", "freq"), key=lambda k: per_step[k])
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp64_arith = sm_count * FP64_LANES_PER_SM * 2 * sm_mhz * 1e6
+        fp64_note = {"probe_tflops": fp64_probe / 1e12, "arithmetic_tflops": fp64_arith / 1e12,
+                     "arithmetic": f"{sm_count} SMs x {FP64_LANES_PER_SM} FP64 lanes x 2 flop x {sm_mhz:.0f} MHz (median "
+                                   f"SM clock under load)",
+                     "frac_uses": "the live DFMA probe (nfh_probe_fp64); frac_of_arithmetic is given beside it"}
         traffic = ncu_traffic() or {}
         t_estep = traffic.get("estep") and traffic["estep"] * rank_units
-        t_freq = traffic.get("freq") and traffic["freq"] * freq_units
-        t_lkl = traffic.get("lkl_batch_per_group_site") and traffic["lkl_batch_per_group_site"] * rank_units  # a round with every individual active
-        roof_estep = {"kernel": "estep (tile_products + carries + apply)", "bound": "hbm", "achieved": estep_gbs,
-                      "peak": hbm_peak, "unit": "GB/s", "frac": estep_gbs / hbm_peak, "traffic": t_estep,
-                      "peak_source": peak_src, "ms_standalone": estep_alone_ms, "ms_per_step": per_step["estep"],
-                      "note": "achieved/frac are of the stand-alone E-step (products + carries + apply); inside an EM "
-                              "iteration the forward products are shared with the first objective round "
-                              "(nfh_estep_with_batch) and ms_per_step covers carries + apply"}
-        roof_freq = {"kernel": "freq_emission_warp", "bound": "fp64", "achieved": freq_tf,
-                     "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": freq_tf / (fp64_peak / 1e12),
-                     "traffic": t_freq, "passes_per_site": passes_per_site,
-                     "bound_note": "FP64 CUDA-core pipe (DFMA), not tensor cores: the work is per-individual rational "
-                                   "functions with no dense contraction",
-                     "instruction_mix_ceiling": FREQ_FLOPS_PER_IND_PASS / (2 * FREQ_INSTR_PER_IND_PASS),
-                     "operand_fetch_note": "DFMA with 3 register operands issues every 3.06 cycles, not 2 "
-                                           "(profiles/microbench/fp64_operands.cu)", "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA",
-                     "ms_per_step": per_step["freq"]}
-        roof_lkl = {"kernel": "lkl_tile_products", "bound": "fp64", "achieved": lkl_tf, "peak": fp64_peak / 1e12,
-                    "unit": "TFLOP/s", "frac": lkl_tf / (fp64_peak / 1e12), "traffic": t_lkl,
-                    "peak_source": "measured live: DFMA probe kernel", "ms_per_step": per_step["lkl_batch"]}
-        roofs = {"estep": roof_estep, "freq": roof_freq, "lkl_batch": roof_lkl}
+        roof_estep = {"kernel": "estep (chunk_products + tile_carries + chunk_apply)", "bound": "hbm",
+                      "achieved": estep_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": estep_gbs / hbm_peak,
+                      "traffic": t_estep, "peak_source": peak_src, "ms_standalone": estep_alone_ms,
+                      "ms_per_step": per_step["estep"], "n_sites": S, "n_ind": n_own,
+                      "note": "achieved/frac are of the stand-alone E-step (products + carries + apply) at 24 B per "
+                              "individual-site; inside a free-parameter EM iteration the forward products are shared "
+                              "with the first objective round (nfh_estep_with_batch) and ms_per_step covers carries + "
+                              "apply"}
+        roofs = {"estep": roof_estep}
+        if not args.fixed:
+            passes_per_site = site_passes / max(ctx.sites_owned * args.steps, 1)
+            freq_tf = FREQ_FLOPS_PER_IND_PASS * passes_per_site * freq_units / (per_step["freq"] * 1e-3) / 1e12
+            evals_step = evals / args.steps
+            lkl_flops = (LKL_FLOPS_PER_IND_SITE_POINT + 0.6 * EXP_FLOPS) * evals_step * S
+            lkl_tf = lkl_flops / (per_step["lkl_batch"] * 1e-3) / 1e12 if per_step["lkl_batch"] > 0 else 0.0
+            t_freq = traffic.get("freq") and traffic["freq"] * freq_units
+            t_lkl = traffic.get("lkl_batch_per_group_site") and traffic["lkl_batch_per_group_site"] * rank_units
+            roofs["freq"] = {
+                "kernel": "freq_emission_*", "bound": "fp64", "achieved": freq_tf, "peak": fp64_probe / 1e12,
+                "unit": "TFLOP/s", "frac": freq_tf / (fp64_probe / 1e12), "frac_of_arithmetic": freq_tf / (fp64_arith / 1e12),
+                "traffic": t_freq, "passes_per_site": passes_per_site,
+                "bound_note": "FP64 CUDA-core pipe (DFMA), not tensor cores: the work is per-individual rational "
+                              "functions with no dense contraction",
+                "instruction_mix_ceiling": FREQ_FLOPS_PER_IND_PASS / (2 * FREQ_INSTR_PER_IND_PASS),
+                "operand_fetch_note": "DFMA with 3 register operands issues every 3.06 cycles, not 2 "
+                                      "(profiles/microbench/fp64_operands.cu)",
+                "peak_source": "measured live: DFMA probe kernel (nfh_probe_fp64), 2 flop/DFMA", "ms_per_step": per_step["freq"]}
+            roofs["lkl_batch"] = {
+                "kernel": "lkl_tile_products", "bound": "fp64", "achieved": lkl_tf, "peak": fp64_probe / 1e12,
+                "unit": "TFLOP/s", "frac": lkl_tf / (fp64_probe / 1e12), "frac_of_arithmetic": lkl_tf / (fp64_arith / 1e12),
+                "traffic": t_lkl, "peak_source": "measured live: DFMA probe kernel", "ms_per_step": per_step["lkl_batch"],
+                "flop_note": "flops counted at the table tier of kappa (13 instructions); tiles in the polynomial tier "
+                             "execute fewer, so this over-states their work"}
+        dominant = max(roofs, key=lambda k: roofs[k]["ms_per_step"])
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"configs[1] per GPU: {args.n_ind} individuals x {S} sites, depth-2 GL, "
-                                   f"--freq_est 1, start --freq 0.1 --indF 0.1,0.2; {N_total} individuals total",
-                       "step": "one EM iteration = E-step + lockstep BFGS(F,alpha) + freq EM + emission refresh",
-                       "l2": "inputs per step (GL+emission+posterior = 4.0 GB per GPU) exceed the 126 MB L2",
+            "config": {"workload": workload_text(args, N_total),
+                       "step": ("one fixed-parameter EM iteration = forward-backward E-step with posteriors"
+                                if args.fixed else
+                                "one EM iteration = E-step + lockstep BFGS(F,alpha) + freq EM + emission refresh"),
+                       "l2": f"inputs per step ({(40 if not args.fixed else 16) * rank_units / 1e9:.1f} GB per GPU) "
+                             f"exceed the 126 MB L2",
                        "parallelism": f"individuals sharded x{world}, sites sharded x{world} for the freq stage",
-                       "exchange": exchange},
-            "roofline": roofs[dominant], "roofline_estep": roof_estep, "roofline_freq": roof_freq,
-            "roofline_lkl_batch": roof_lkl,
+                       "exchange": exchange,
+                       "legs": "device-timed and end-to-end legs both start from reset state + the same warm-up"},
+            "roofline": roofs[dominant], "roofline_estep": roof_estep,
             "kernel_ms_per_step": per_step,
-            "bfgs": {"objective_evals_per_step": evals_step, "rounds_per_step": rounds / args.steps},
+            "fp64_peak": fp64_note,
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
-                    "note": "GL upload and final posterior/path download are one-off per run, see run_overheads"},
-            "run_overheads": {"gl_upload_s": t_upload, "gl_bytes": gl_bytes, "generate_s": t_gen,
-                              "viterbi_posterior_download_s": t_final},
+                    "note": "GL upload and final posterior/path download are one-off per run, see e2e_full_run"},
+            "e2e_full_run": {"seconds": t_full, "iterations": 2 * (args.steps + args.warmup),
+                             "covers": "context creation, synthetic GL generation on the GPU, nfh_upload_gl, both "
+                                       "timed legs with their warm-ups, emission refresh with e0, Viterbi, path and "
+                                       "posterior download", "generate_s": t_gen, "gl_upload_s": t_upload,
+                             "gl_bytes": gl_bytes, "final_refresh_viterbi_download_s": t_final_ms / 1e3},
+            "viterbi": {"kernel_ms": vit_ms, "ind_sites_per_s": float(N_total) * S / (vit_ms * 1e-3) if vit_ms > 0 else None,
+                        "refresh_with_e0_s": t2 - t1, "decode_and_path_download_s": t3 - t2,
+                        "posterior_download_s": t4 - t3},
             "gpu_launches": int(launches), "clocks": clocks,
             "final_loglkl_rank0": float(np.sum(lk)), "viterbi_ibd_fraction_rank0": float(path.mean()),
         }
+        if not args.fixed:
+            out["roofline_freq"] = roofs["freq"]
+            out["roofline_lkl_batch"] = roofs["lkl_batch"]
+            out["bfgs"] = {"objective_evals_per_step": evals / args.steps, "rounds_per_step": rounds / args.steps}
+        if parity is not None:
+            out["parity_check"] = parity
         if not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = reference_arm(args, as_cpu_baseline=True)
@@ -398,6 +517,7 @@ def main():
                                        "sample": f"unavailable: {ex}"}
         print(json.dumps(out), flush=True)
     del post, path
+    barrier()                                   # peers may still gather from this rank's windows
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -60,6 +60,8 @@ const char *nfh_strerror(int status);
 const char *nfh_last_error(const nfh_ctx *ctx);
 /* Library build tag, e.g. "sm_100a"; also proves the .so loaded. */
 const char *nfh_build_info(void);
+/* Number of CUDA devices visible to this process (0 without a driver or a GPU). */
+int nfh_device_count(void);
 /* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t nfh_kernel_launches(const nfh_ctx *ctx);
 

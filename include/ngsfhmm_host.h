@@ -41,6 +41,40 @@ int nfh_host_estep_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, doubl
 int nfh_host_em_iteration(nfh_ctx *ctx, double *indF, double *alpha, int F_fixed, int alpha_fixed, int freq_est,
                           double *ind_lkl_out, double *freq_out, uint64_t stats_out[3]);
 
+/* ---------------------------------------------------------------------------
+ * One process, several GPUs.  Replaces main() -> EM() -> iter_EM() (ngsF-HMM.cpp:27-171, EM.cpp:27-135,
+ * EM.cpp:139-289) when the individuals are sharded over the GPUs of one box: a group owns one context per
+ * rank (devices[r]; the same ordinal may repeat, which runs the multi-rank geometry on one GPU), one host
+ * thread per rank drives its context, the stages are ordered by host joins.  All host arrays are GLOBAL:
+ * indF / alpha / ind_lkl [n_ind_total], freq [n_sites], path and posterior [n_ind_total][n_sites],
+ * log_gl site-major [n][n_ind_total][3] as in the input file.
+ * fused_exchange != 0: the E-step and frequency kernels store straight into the windows of the rank that owns
+ * the data next (peer memory, NVLink between devices); 0: block copies between the windows.
+ * ------------------------------------------------------------------------- */
+typedef struct nfh_group nfh_group;
+int nfh_group_create(nfh_group **out, int n_ranks, const int *devices, uint64_t n_ind_total, uint64_t n_sites,
+                     int fused_exchange);
+void nfh_group_destroy(nfh_group *g);
+const char *nfh_group_last_error(const nfh_group *g);
+int nfh_group_size(const nfh_group *g);
+nfh_ctx *nfh_group_ctx(nfh_group *g, int rank);
+int nfh_group_upload_gl(nfh_group *g, const double *log_gl, uint64_t first_site, uint64_t n);
+int nfh_group_upload_pos_dist(nfh_group *g, const double *dist_mb);
+int nfh_group_set_freq(nfh_group *g, const double *freq);
+int nfh_group_set_ind_params(nfh_group *g, const double *indF, const double *alpha);
+/* calc_emission over everything (+ e0 for Viterbi), exchanged and reduced across the ranks */
+int nfh_group_refresh_emissions(nfh_group *g, int with_e0);
+/* "--freq e": est_maf with F = 0 for everyone (parse_args.cpp:316-318) + emission refresh */
+int nfh_group_freq_init(nfh_group *g, double *freq_out);
+/* iter_EM (EM.cpp:139-289) over all ranks; stats_out = {max rounds, total evaluations, max rounds of one individual} */
+int nfh_group_em_iteration(nfh_group *g, double *indF, double *alpha, int F_fixed, int alpha_fixed, int freq_est,
+                           double *ind_lkl_out, double *freq_out, uint64_t stats_out[3]);
+int nfh_group_estep(nfh_group *g, double *ind_lkl_out);
+int nfh_group_viterbi(nfh_group *g, char *path_out);
+int nfh_group_get_posterior(nfh_group *g, double *marg1_out);
+int nfh_group_get_freq(nfh_group *g, double *freq_out);
+int nfh_group_geno_posterior(nfh_group *g, const char *path_all, double *geno_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,4 +5,4 @@ synthetic inputs, multi-rank exchange through torch.distributed).  There is no
 CPU fallback: without the compiled library and a CUDA device the calls raise.
 """
 from .api import Context, NfhError, library_path, load_library, build_library  # noqa: F401
-from .em import EmRank, load_host_library, run_em  # noqa: F401,E402
+from .em import EmRank, Group, load_host_library, run_em  # noqa: F401,E402

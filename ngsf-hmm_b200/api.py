@@ -29,7 +29,7 @@ EXPORTS = [
     "nfh_emission_refresh", "nfh_estep", "nfh_lkl_batch", "nfh_freq_update", "nfh_viterbi", "nfh_get_posterior",
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
     "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister", "nfh_estep_with_batch",
-    "nfh_peer_set", "nfh_window_copy_block", "nfh_window_read", "nfh_window_write",
+    "nfh_device_count", "nfh_peer_set", "nfh_window_copy_block", "nfh_window_read", "nfh_window_write",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library():
     L.nfh_last_error.restype = C.c_char_p; L.nfh_last_error.argtypes = [_vp]
     L.nfh_build_info.restype = C.c_char_p
     L.nfh_kernel_launches.restype = u64; L.nfh_kernel_launches.argtypes = [_vp]
+    L.nfh_device_count.restype = cint; L.nfh_device_count.argtypes = []
     L.nfh_ctx_create.restype = cint; L.nfh_ctx_create.argtypes = [C.POINTER(_vp), cint, u64, u64, cint, cint]
     L.nfh_ctx_destroy.restype = None; L.nfh_ctx_destroy.argtypes = [_vp]
     for n in ("nfh_n_ind_local", "nfh_n_ind_owned", "nfh_ind_begin", "nfh_site_block", "nfh_site_begin",

@@ -169,9 +169,19 @@ const char *nfh_build_info(void) { return "ngsfhmm_b200 sm_100a fp64 (no CPU fal
 
 uint64_t nfh_kernel_launches(const nfh_ctx *ctx) { return ctx->launches; }
 
+int nfh_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_sites, int n_ranks, int rank) {
   if (!out || n_ind_total == 0 || n_sites == 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks) {
     g_create_err = "nfh_ctx_create: bad geometry";
+    return NFH_ERR_ARG;
+  }
+  if (n_ind_total > 65535) {   // individuals index grid.y of several kernels; the reference's print_iter has the same limit (uint16_t, EM.cpp:306)
+    g_create_err = "nfh_ctx_create: at most 65535 individuals";
     return NFH_ERR_ARG;
   }
   int n_dev = 0;
@@ -310,22 +320,33 @@ int nfh_upload_gl(nfh_ctx *ctx, const double *log_gl, uint64_t first_site, uint6
   const uint64_t per_site = N * 3 * sizeof(double);
   uint64_t chunk = kStageBytes / per_site;
   if (chunk == 0) return fail(ctx, NFH_ERR_ARG, "nfh_upload_gl: one site exceeds the staging buffer");
+  // where the caller's array lives: page-locked host memory is copied from directly, pageable host memory goes
+  // through the pinned staging buffer, device memory (a generator that already ran on the GPU) is ingested in place
   cudaPointerAttributes attr;
-  bool src_pinned = cudaPointerGetAttributes(&attr, log_gl) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  const bool known = cudaPointerGetAttributes(&attr, log_gl) == cudaSuccess;
   cudaGetLastError();
+  const bool src_pinned = known && attr.type == cudaMemoryTypeHost;
+  const bool src_device = known && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  if (src_device && attr.type == cudaMemoryTypeDevice && attr.device != ctx->device)
+    return fail(ctx, NFH_ERR_ARG, "nfh_upload_gl: device array lives on another GPU");
   for (uint64_t done = 0; done < n; done += chunk) {
     const uint64_t m = std::min(chunk, n - done);
     const double *src = log_gl + done * N * 3;
-    if (!src_pinned) {
-      NFH_CUDA(cudaStreamSynchronize(ctx->stream));   // staging buffer is reused
-      memcpy(ctx->h_stage, src, m * per_site);
-      src = (const double *) ctx->h_stage;
+    const double *staged = (const double *) ctx->d_stage;
+    if (src_device) {
+      staged = src;
+    } else {
+      if (!src_pinned) {
+        NFH_CUDA(cudaStreamSynchronize(ctx->stream));   // staging buffer is reused
+        memcpy(ctx->h_stage, src, m * per_site);
+        src = (const double *) ctx->h_stage;
+      }
+      NFH_CUDA(cudaMemcpyAsync(ctx->d_stage, src, m * per_site, cudaMemcpyHostToDevice, ctx->stream));
     }
-    NFH_CUDA(cudaMemcpyAsync(ctx->d_stage, src, m * per_site, cudaMemcpyHostToDevice, ctx->stream));
     {
       FamilyScope fs(ctx, kFamIngest, 1);
-      launch_gl_ingest((const double *) ctx->d_stage, m, N, first_site - ctx->site_begin + done, ctx->site_block,
-                       ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->stream);
+      launch_gl_ingest(staged, m, N, first_site - ctx->site_begin + done, ctx->site_block, ctx->gl[0], ctx->gl[1],
+                       ctx->gl[2], ctx->stream);
     }
     NFH_CUDA(cudaGetLastError());
   }
@@ -637,19 +658,24 @@ int nfh_geno_posterior(nfh_ctx *ctx, const char *path_all, double *geno_out) {
   const uint64_t N = ctx->n_ind_total;
   char *d_path = nullptr;
   NFH_CUDA(cudaMalloc((void **) &d_path, N * ctx->sites_owned));
-  NFH_CUDA(cudaMemcpyAsync(d_path, path_all, N * ctx->sites_owned, cudaMemcpyHostToDevice, ctx->stream));
-  const uint64_t per_site = N * 3 * sizeof(double);
-  const uint64_t chunk = std::max<uint64_t>(1, kStageBytes / per_site);
-  for (uint64_t s0 = 0; s0 < ctx->sites_owned; s0 += chunk) {
-    const uint64_t m = std::min(chunk, ctx->sites_owned - s0);
-    launch_geno_posterior(ctx->gl[0] + s0, ctx->gl[1] + s0, ctx->gl[2] + s0, ctx->freq + s0, d_path + s0, N,
-                          ctx->site_block, ctx->sites_owned, m, (double *) ctx->d_stage, ctx->stream);
-    ctx->launches++;
-    NFH_CUDA(cudaMemcpyAsync(geno_out + s0 * N * 3, ctx->d_stage, m * per_site, cudaMemcpyDeviceToHost, ctx->stream));
-    NFH_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
-  cudaFree(d_path);
-  return NFH_OK;
+  auto body = [&]() -> int {
+    NFH_CUDA(cudaMemcpyAsync(d_path, path_all, N * ctx->sites_owned, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t per_site = N * 3 * sizeof(double);
+    const uint64_t chunk = std::max<uint64_t>(1, kStageBytes / per_site);
+    for (uint64_t s0 = 0; s0 < ctx->sites_owned; s0 += chunk) {
+      const uint64_t m = std::min(chunk, ctx->sites_owned - s0);
+      launch_geno_posterior(ctx->gl[0] + s0, ctx->gl[1] + s0, ctx->gl[2] + s0, ctx->freq + s0, d_path + s0, N,
+                            ctx->site_block, ctx->sites_owned, m, (double *) ctx->d_stage, ctx->stream);
+      ctx->launches++;
+      NFH_CUDA(cudaGetLastError());
+      NFH_CUDA(cudaMemcpyAsync(geno_out + s0 * N * 3, ctx->d_stage, m * per_site, cudaMemcpyDeviceToHost, ctx->stream));
+      NFH_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return NFH_OK;
+  };
+  const int rc = body();
+  cudaFree(d_path);      // on every path
+  return rc;
 }
 
 static double *window_base(nfh_ctx *ctx, int window, uint64_t *bytes) {

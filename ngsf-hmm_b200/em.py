@@ -272,3 +272,136 @@ def run_em(runner: EmRank, indF, alpha, *, min_iters=10, max_iters=100, min_epsi
     runner.ctx.set_ind_params(indF, alpha)
     path = runner.ctx.viterbi()
     return dict(iterations=it, tot_lkl=tot, ind_lkl=lk, freq=fr, path=path)
+
+
+class Group:
+    """One process driving several device contexts (libngsfhmm_host.so, nfh_group_*): the multi-GPU form of
+    the reference's main() -> EM() -> iter_EM() (ngsF-HMM.cpp:27-171, EM.cpp:27-135, EM.cpp:139-289).
+
+    ``devices[r]`` is the CUDA ordinal of rank r; the same ordinal may repeat, which runs the multi-rank
+    geometry (individuals sharded for the recursions, sites sharded for the frequency EM, posteriors and
+    emission ratios crossing between the two) on one GPU.  All arrays are global: indF / alpha / ind_lkl
+    [n_ind], freq [n_sites], path / posterior [n_ind, n_sites].
+    """
+
+    def __init__(self, n_ind, n_sites, devices, fused_exchange=True, *, indF_fixed=False, alpha_fixed=False,
+                 freq_est=1):
+        H = load_host_library()
+        u64, cint, vp = C.c_uint64, C.c_int, C.c_void_p
+        u64p = C.POINTER(u64)
+        sig = {
+            "nfh_group_create": [C.POINTER(vp), cint, C.POINTER(cint), u64, u64, cint],
+            "nfh_group_upload_gl": [vp, vp, u64, u64], "nfh_group_upload_pos_dist": [vp, _dp],
+            "nfh_group_set_freq": [vp, _dp], "nfh_group_set_ind_params": [vp, _dp, _dp],
+            "nfh_group_refresh_emissions": [vp, cint], "nfh_group_freq_init": [vp, _dp],
+            "nfh_group_em_iteration": [vp, _dp, _dp, cint, cint, cint, _dp, _dp, u64p],
+            "nfh_group_estep": [vp, _dp], "nfh_group_viterbi": [vp, vp], "nfh_group_get_posterior": [vp, _dp],
+            "nfh_group_get_freq": [vp, _dp], "nfh_group_geno_posterior": [vp, vp, _dp], "nfh_group_size": [vp],
+        }
+        for name, argtypes in sig.items():
+            fn = getattr(H, name); fn.restype = cint; fn.argtypes = argtypes
+        H.nfh_group_destroy.restype = None; H.nfh_group_destroy.argtypes = [vp]
+        H.nfh_group_last_error.restype = C.c_char_p; H.nfh_group_last_error.argtypes = [vp]
+        H.nfh_group_ctx.restype = vp; H.nfh_group_ctx.argtypes = [vp, cint]
+        self.H = H
+        self.n_ind, self.n_sites, self.n_ranks = int(n_ind), int(n_sites), len(devices)
+        self.indF_fixed, self.alpha_fixed, self.freq_est = indF_fixed, alpha_fixed, freq_est
+        self.stats = np.zeros(3, dtype=np.uint64)
+        self.total_evals = 0
+        self.total_rounds = 0
+        dev = (cint * len(devices))(*devices)
+        h = vp()
+        rc = H.nfh_group_create(C.byref(h), len(devices), dev, self.n_ind, self.n_sites, int(fused_exchange))
+        self.h = h
+        self._chk(rc)
+
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self.H.nfh_group_last_error(self.h).decode() if self.h else ""
+            raise api.NfhError(rc, msg or api.load_library().nfh_strerror(rc).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.H.nfh_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def upload_gl(self, log_gl_site_major, first_site=0):
+        g = np.ascontiguousarray(log_gl_site_major, dtype=np.float64)
+        self._chk(self.H.nfh_group_upload_gl(self.h, g.ctypes.data, first_site, g.shape[0]))
+
+    def upload_pos_dist(self, dist_mb):
+        d = np.ascontiguousarray(dist_mb, dtype=np.float64)
+        assert d.shape == (self.n_sites,)
+        self._chk(self.H.nfh_group_upload_pos_dist(self.h, d.ctypes.data_as(_dp)))
+
+    def set_freq(self, freq):
+        f = np.ascontiguousarray(np.broadcast_to(freq, (self.n_sites,)), dtype=np.float64)
+        self._chk(self.H.nfh_group_set_freq(self.h, f.ctypes.data_as(_dp)))
+
+    def set_ind_params(self, indF, alpha):
+        F = np.ascontiguousarray(np.broadcast_to(indF, (self.n_ind,)), dtype=np.float64)
+        a = np.ascontiguousarray(np.broadcast_to(alpha, (self.n_ind,)), dtype=np.float64)
+        self._chk(self.H.nfh_group_set_ind_params(self.h, F.ctypes.data_as(_dp), a.ctypes.data_as(_dp)))
+
+    def refresh_emissions(self, with_e0=False):
+        self._chk(self.H.nfh_group_refresh_emissions(self.h, int(with_e0)))
+
+    def freq_init(self):
+        f = np.empty(self.n_sites)
+        self._chk(self.H.nfh_group_freq_init(self.h, f.ctypes.data_as(_dp)))
+        return f
+
+    def iteration(self, indF, alpha, want_freq=True):
+        """One EM iteration over all ranks; indF / alpha (float64, n_ind) are updated in place."""
+        lk = np.empty(self.n_ind)
+        fr = np.empty(self.n_sites) if (want_freq and self.freq_est) else None
+        rc = self.H.nfh_group_em_iteration(self.h, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
+                                           int(self.indF_fixed), int(self.alpha_fixed), int(self.freq_est),
+                                           lk.ctypes.data_as(_dp), fr.ctypes.data_as(_dp) if fr is not None else None,
+                                           self.stats.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self._chk(rc)
+        self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
+        return lk, fr
+
+    def estep(self):
+        lk = np.empty(self.n_ind)
+        self._chk(self.H.nfh_group_estep(self.h, lk.ctypes.data_as(_dp)))
+        return lk
+
+    def viterbi(self):
+        path = np.zeros((self.n_ind, self.n_sites), dtype=np.int8)
+        self._chk(self.H.nfh_group_viterbi(self.h, path.ctypes.data))
+        return path
+
+    def get_posterior(self):
+        m = np.empty((self.n_ind, self.n_sites))
+        self._chk(self.H.nfh_group_get_posterior(self.h, m.ctypes.data_as(_dp)))
+        return m
+
+    def get_freq(self):
+        f = np.empty(self.n_sites)
+        self._chk(self.H.nfh_group_get_freq(self.h, f.ctypes.data_as(_dp)))
+        return f
+
+    def geno_posterior(self, path_all):
+        p = np.ascontiguousarray(path_all, dtype=np.int8)
+        out = np.empty((self.n_sites, self.n_ind, 3))
+        self._chk(self.H.nfh_group_geno_posterior(self.h, p.ctypes.data, out.ctypes.data_as(_dp)))
+        return out
+
+    # run_em() treats a Group like an EmRank
+    @property
+    def ctx(self):
+        return self

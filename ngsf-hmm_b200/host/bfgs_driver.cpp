@@ -112,8 +112,12 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
   // stops before its first evaluation)
   bool estep_pending = estep_lkl_out != nullptr;
   if (estep_pending) {
+    // ... and when the optimiser's first centre point IS the parameter point the context holds: start()
+    // projects x0 into the box (F = 0, F = 1 or alpha > 10 move), while the reference runs forward/backward
+    // at the unprojected parameters (EM.cpp:151-185) and only lets setulb_ project for the optimiser
     bool all_active = true;
-    for (uint64_t i = 0; i < n_ind; i++) all_active = all_active && slots[i].active;
+    for (uint64_t i = 0; i < n_ind; i++)
+      all_active = all_active && slots[i].active && slots[i].opt->x()[0] == indF[i] && slots[i].opt->x()[1] == alpha[i];
     if (!all_active) {
       int rc = nfh_estep(ctx, estep_lkl_out);
       if (rc != NFH_OK) return rc;

@@ -1,7 +1,7 @@
 // em_loop.cpp - iteration control of the drop-in binary (EM(), EM.cpp:27-135):
 // stop rule, per-iteration report, --log dumps, signal handling, final Viterbi.
 // Every iteration body is one call into the host library
-// (nfh_host_em_iteration = iter_EM on the device).
+// (nfh_group_em_iteration = iter_EM on the device(s) of the group).
 #include <signal.h>
 
 #include <cmath>
@@ -60,7 +60,8 @@ void run_em(RunState &st, bool write_final) {
   install_handlers();
 
   // the frequencies come back every iteration (8 bytes per site): page-lock their host array
-  const bool pinned = nfh_host_register(st.ctx, st.freq.data(), S * sizeof(double)) == NFH_OK;
+  nfh_ctx *ctx0 = nfh_group_ctx(st.grp, 0);
+  const bool pinned = nfh_host_register(ctx0, st.freq.data(), S * sizeof(double)) == NFH_OK;
 
   uint64_t iter = 0;
   double max_eps = -INFINITY;
@@ -77,7 +78,7 @@ void run_em(RunState &st, bool write_final) {
          iter < o.max_iters && g_keep_going) {
     if (o.log && (iter == 1 || iter % o.log == 0)) {
       if (o.verbose >= 1) printf("==> Printing current iteration parameters\n");
-      check(st, nfh_get_posterior(st.ctx, st.marg1.data()), "nfh_get_posterior");
+      check(st, nfh_group_get_posterior(st.grp, st.marg1.data()), "nfh_get_posterior");
       write_outputs(st);
     }
     const time_t t0 = time(nullptr);
@@ -91,8 +92,8 @@ void run_em(RunState &st, bool write_final) {
                              : "==> Estimating allele frequencies and calculating emission probabilities\n");
 
     uint64_t stats[3] = {0, 0, 0};
-    check(st, nfh_host_em_iteration(st.ctx, st.indF.data(), st.alpha.data(), o.indF_fixed, o.alpha_fixed, o.freq_est,
-                                    st.ind_lkl.data(), st.freq.data(), stats),
+    check(st, nfh_group_em_iteration(st.grp, st.indF.data(), st.alpha.data(), o.indF_fixed, o.alpha_fixed, o.freq_est,
+                                     st.ind_lkl.data(), st.freq.data(), stats),
           "iter_EM");
     if (o.verbose >= 4 && !(o.indF_fixed && o.alpha_fixed))
       for (uint64_t i = 0; i < N; i++) printf("\t%.10f\t%f\n", st.indF[i], st.alpha[i]);
@@ -121,15 +122,15 @@ void run_em(RunState &st, bool write_final) {
   }
   if (iter >= o.max_iters) printf("WARN: Maximum number of iterations reached! Check if analysis converged... \n");
 
-  if (pinned) nfh_host_unregister(st.ctx, st.freq.data());
+  if (pinned) nfh_host_unregister(ctx0, st.freq.data());
 
   if (o.verbose >= 1) printf("\n==> Decoding most probable path (Viterbi)\n");
-  check(st, nfh_set_ind_params(st.ctx, st.indF.data(), st.alpha.data()), "nfh_set_ind_params");
-  check(st, nfh_emission_refresh(st.ctx, 1), "nfh_emission_refresh");
-  check(st, nfh_viterbi(st.ctx, st.path.data()), "nfh_viterbi");
+  check(st, nfh_group_set_ind_params(st.grp, st.indF.data(), st.alpha.data()), "nfh_set_ind_params");
+  check(st, nfh_group_refresh_emissions(st.grp, 1), "nfh_emission_refresh");
+  check(st, nfh_group_viterbi(st.grp, st.path.data()), "nfh_viterbi");
 
   if (o.verbose >= 1) printf("Final logLkl: %f\n", st.tot_lkl);
-  check(st, nfh_get_posterior(st.ctx, st.marg1.data()), "nfh_get_posterior");
+  check(st, nfh_group_get_posterior(st.grp, st.marg1.data()), "nfh_get_posterior");
   if (write_final) {
     if (o.verbose >= 1) printf("Printing final results\n");
     write_outputs(st);

@@ -49,7 +49,7 @@ int main(int argc, char **argv) {
     write_outputs(st);
   }
   if (st.opt.verbose >= 1) printf("Freeing memory...\n");
-  nfh_ctx_destroy(st.ctx);
+  nfh_group_destroy(st.grp);
   if (st.opt.verbose >= 1) printf("Done!\n");
   return 0;
 }

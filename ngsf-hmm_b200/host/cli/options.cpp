@@ -45,9 +45,10 @@ void parse_options(Options &o, int argc, char **argv) {
       {"min_epsilon", required_argument, nullptr, 'E'}, {"n_threads", required_argument, nullptr, 'x'},
       {"verbose", required_argument, nullptr, 'V'},   {"seed", required_argument, nullptr, 'S'},
       {"device", required_argument, nullptr, 'D'},    {"n_rep", required_argument, nullptr, 'R'},
+      {"n_gpus", required_argument, nullptr, 'U'},
       {nullptr, 0, nullptr, 0}};
   int c;
-  while ((c = getopt_long_only(argc, argv, "g:Z:lLn:s:Gf:F:e:i:IAo:X:b:m:M:E:x:V:S:D:R:", table, nullptr)) != -1) {
+  while ((c = getopt_long_only(argc, argv, "g:Z:lLn:s:Gf:F:e:i:IAo:X:b:m:M:E:x:V:S:D:R:U:", table, nullptr)) != -1) {
     switch (c) {
       case 'g': o.geno = optarg; o.have_geno = true; break;
       case 'Z': o.pos = optarg; o.have_pos = true; break;
@@ -73,6 +74,7 @@ void parse_options(Options &o, int argc, char **argv) {
       case 'S': o.seed = (unsigned) atoi(optarg); break;
       case 'D': o.device = atoi(optarg); break;
       case 'R': o.n_rep = (unsigned) atoi(optarg); break;
+      case 'U': o.n_gpus = atoi(optarg); break;
       default: exit(-1);
     }
   }
@@ -108,6 +110,7 @@ void parse_options(Options &o, int argc, char **argv) {
   if (o.min_iters < 1 || o.max_iters < 1 || o.min_iters >= o.max_iters) fatal(fn, "invalid number of iterations!");
   if (o.n_threads < 1) fatal(fn, "invalid number of threads!");
   if (o.n_rep < 1) fatal(fn, "invalid number of replicates!");
+  if (o.n_gpus < 1 || o.n_gpus > 8) fatal(fn, "invalid number of GPUs (--n_gpus 1..8)!");
   {
     const unsigned hw = std::thread::hardware_concurrency();
     o.host_threads = o.n_threads_given ? o.n_threads : std::max(1u, std::min(hw ? hw : 1u, 16u));

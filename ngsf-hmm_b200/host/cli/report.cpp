@@ -25,8 +25,6 @@ namespace {
 FILE *open_out(const std::string &name, const char *what) {
   FILE *fh = fopen(name.c_str(), "wb");
   if (!fh) fatal("print_iter", what);
-  static char big[1 << 20];
-  (void) big;
   setvbuf(fh, nullptr, _IOFBF, 1 << 22);
   return fh;
 }
@@ -95,8 +93,8 @@ void write_outputs(RunState &st) {
   fh = open_out(o.out + ".geno", "cannot open GENO output file!");
   const size_t n_geno = S * N * 3;
   std::unique_ptr<double[]> geno(new double[n_geno]);      // no fill pass: the device writes every value
-  check(st, nfh_set_freq(st.ctx, st.freq.data()), "nfh_set_freq");
-  check(st, nfh_geno_posterior(st.ctx, st.path.data(), geno.get()), "nfh_geno_posterior");
+  check(st, nfh_group_set_freq(st.grp, st.freq.data()), "nfh_set_freq");
+  check(st, nfh_group_geno_posterior(st.grp, st.path.data(), geno.get()), "nfh_geno_posterior");
   if (fwrite(geno.get(), sizeof(double), n_geno, fh) != n_geno)
     fatal("print_iter", "cannot write GENO output file!");
   fclose(fh);

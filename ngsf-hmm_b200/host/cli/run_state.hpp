@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "ngsfhmm_b200.h"
+#include "ngsfhmm_host.h"
 
 namespace nfh_cli {
 
@@ -25,7 +25,9 @@ struct Options {   // one field per command-line flag of the reference (parse_ar
   unsigned host_threads = 1;   // threads for parsing / formatting: --n_threads when given, else the host's cores (<= 16)
   double min_epsilon = 1e-5;
   bool have_geno = false, have_pos = false, have_out = false;
-  int device = 0;          // --device (extension; not a reference flag)
+  int device = 0;          // --device (extension; not a reference flag): first CUDA ordinal used
+  int n_gpus = 1;          // --n_gpus (extension): individuals sharded over devices device .. device + n_gpus - 1 of this
+                           // box, one context per GPU driven by this one process (nfh_group_*, ngsfhmm_host.h)
   unsigned n_rep = 1;      // --n_rep (extension): replicates of the whole EM from different --seed values on one
                            // ingest and one GL upload; the best final logLkl is written (what ngsF-HMM.sh does
                            // with one process, one parse and one upload per replicate)
@@ -33,7 +35,7 @@ struct Options {   // one field per command-line flag of the reference (parse_ar
 
 struct RunState {
   Options opt;
-  nfh_ctx *ctx = nullptr;
+  nfh_group *grp = nullptr;           // one context per GPU (a group of one is the single-GPU run)
   std::vector<double> dist_mb;        // n_sites
   std::unique_ptr<double[]> log_gl;   // site-major n_sites x n_ind x 3, normalised natural-log GL (2.4 GB at
                                       // configs[1]: allocated without a fill pass)

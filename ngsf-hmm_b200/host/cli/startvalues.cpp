@@ -67,7 +67,8 @@ void chomp(char *s) {
 
 void check(RunState &st, int rc, const char *where) {
   if (rc == NFH_OK) return;
-  const char *msg = st.ctx ? nfh_last_error(st.ctx) : nfh_last_error(nullptr);
+  const char *msg = st.grp ? nfh_group_last_error(st.grp) : nfh_last_error(nullptr);
+  if (!msg || !*msg) msg = nfh_last_error(nullptr);
   if (!msg || !*msg) msg = nfh_strerror(rc);
   switch (rc) {
     case NFH_ERR_NAN: fatal("forward", "invalid Lkl found!");          // HMM.cpp:18-21
@@ -78,9 +79,18 @@ void check(RunState &st, int rc, const char *where) {
 
 void create_device_state(RunState &st) {
   Options &o = st.opt;
-  check(st, nfh_ctx_create(&st.ctx, o.device, o.n_ind, o.n_sites, 1, 0), "nfh_ctx_create");
-  check(st, nfh_upload_pos_dist(st.ctx, st.dist_mb.data()), "nfh_upload_pos_dist");
-  check(st, nfh_upload_gl(st.ctx, st.log_gl.get(), 0, o.n_sites), "nfh_upload_gl");
+  // rank r of the group runs on device o.device + r; the kernels exchange posteriors and emission ratios
+  // through peer memory (NVLink), see ngsfhmm_host.h
+  std::vector<int> devices(o.n_gpus);
+  const int visible = nfh_device_count();
+  // NFH_SHARE_DEVICES=1 (testing aid): ranks wrap around the visible devices, so the sharded run can be
+  // exercised on a box with fewer GPUs than ranks
+  const char *share = getenv("NFH_SHARE_DEVICES");
+  for (int r = 0; r < o.n_gpus; r++)
+    devices[r] = (share && *share == '1' && visible > 0) ? (o.device + r) % visible : o.device + r;
+  check(st, nfh_group_create(&st.grp, o.n_gpus, devices.data(), o.n_ind, o.n_sites, 1), "nfh_group_create");
+  check(st, nfh_group_upload_pos_dist(st.grp, st.dist_mb.data()), "nfh_upload_pos_dist");
+  check(st, nfh_group_upload_gl(st.grp, st.log_gl.get(), 0, o.n_sites), "nfh_upload_gl");
 }
 
 void init_start_values(RunState &st, unsigned seed) {
@@ -153,10 +163,10 @@ void init_start_values(RunState &st, unsigned seed) {
 
   if (o.verbose >= 1) printf("==> Calculating initial emission probabilities\n");
   if (estimate) {
-    check(st, nfh_freq_update(st.ctx, 1, 1, st.freq.data()), "nfh_freq_update");   // est_maf with F = 0
+    check(st, nfh_group_freq_init(st.grp, st.freq.data()), "nfh_freq_update");   // est_maf with F = 0
   } else {
-    check(st, nfh_set_freq(st.ctx, st.freq.data()), "nfh_set_freq");
-    check(st, nfh_emission_refresh(st.ctx, 0), "nfh_emission_refresh");
+    check(st, nfh_group_set_freq(st.grp, st.freq.data()), "nfh_set_freq");
+    check(st, nfh_group_refresh_emissions(st.grp, 0), "nfh_emission_refresh");
   }
   st.ind_lkl.assign(N, -INFINITY);
   st.path.assign(N * S, 0);

@@ -173,3 +173,53 @@ def test_one_parameter_fixed(tmp_path, flag):
     _run(REF, common + ["--out", "ref"], str(tmp_path))
     _run(OURS, common + ["--out", "ours"], str(tmp_path))
     _compare(tmp_path, N, S, f_tol=5e-5)
+
+
+def test_call_geno_flag(tmp_path):
+    """GL input with --call_geno (the third input mode of the reference's test matrix, examples/test.sh:28-53;
+    ngsF-HMM.cpp:101-117, gen_func.cpp:886-914): every likelihood triplet collapses to its most likely
+    genotype before the EM."""
+    N, S = 7, 2500
+    d = sim.simulate(N, S, seed=1212, freq=(0.1, 0.5), indF=(0.1, 0.6), alpha=0.02, depth=6.0)
+    sim.write_binary_gl(str(tmp_path / "in.glf"), d.log_gl)
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    common = ["--geno", "in.glf", "--loglkl", "--call_geno", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos",
+              "--freq", "0.1", "--indF", "0.1,0.2", "--min_iters", "3", "--max_iters", "4", "--verbose", "0"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    _run(OURS, common + ["--out", "ours"], str(tmp_path))
+    _compare(tmp_path, N, S, f_tol=5e-5)
+    # and it is not the same run as without the flag
+    _run(OURS, [a for a in common if a != "--call_geno"] + ["--out", "nocall"], str(tmp_path))
+    assert open(tmp_path / "nocall.indF").read() != open(tmp_path / "ours.indF").read()
+
+
+@pytest.mark.parametrize("n_gpus", [2, 3])
+def test_n_gpus_equals_one_gpu(tmp_path, n_gpus):
+    """--n_gpus N (extension): individuals sharded over N device contexts driven by the one process.  The files
+    must equal the single-GPU run's up to the last printed digit of a few values (tile boundaries move with the
+    site-block size).  On a box with fewer GPUs than ranks the ranks share devices (NFH_SHARE_DEVICES=1), which
+    exercises the same sharding, peer stores and reductions."""
+    N, S = 9, 9000
+    d = sim.simulate(N, S, seed=515, freq=(0.1, 0.5), indF=(0.1, 0.6), alpha=0.02, depth=3.0)
+    sim.write_binary_gl(str(tmp_path / "in.glf"), d.log_gl)
+    with open(str(tmp_path / "in.pos"), "w") as fh:               # two chromosomes
+        for s in range(S):
+            chrom = "chr1" if s < 5000 else "chr2"
+            pos = int(d.pos_bp[s]) if s < 5000 else int(d.pos_bp[s] - d.pos_bp[4999])
+            fh.write(f"{chrom}\t{pos}\n")
+    common = ["--geno", "in.glf", "--loglkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "e",
+              "--indF", "0.1,0.2", "--min_iters", "3", "--max_iters", "5", "--verbose", "0"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    env = dict(os.environ, NFH_SHARE_DEVICES="1")
+    p = subprocess.run([OURS] + common + ["--out", "ours", "--n_gpus", str(n_gpus)], cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    _compare(tmp_path, N, S, f_tol=5e-5)
+    _run(OURS, common + ["--out", "one"], str(tmp_path))
+    tot1, F1, a1, fr1 = _parse_indF(str(tmp_path / "one.indF"), N)
+    totn, Fn, an, frn = _parse_indF(str(tmp_path / "ours.indF"), N)
+    assert abs(totn - tot1) <= 1e-11 * abs(tot1)
+    assert np.abs(Fn - F1).max() <= 1e-5 and np.abs(frn - fr1).max() <= 1e-6     # print precision %.5f / %f
+    _, p1, m1 = _parse_ibd(str(tmp_path / "one.ibd"), N)
+    _, pn, mn = _parse_ibd(str(tmp_path / "ours.ibd"), N)
+    assert (p1 != pn).sum() == 0 and np.abs(m1 - mn).max() <= 1.1e-5

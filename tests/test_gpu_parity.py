@@ -407,3 +407,20 @@ def test_estep_with_batch_equals_the_two_calls(oracle):
         with pytest.raises(nfh.NfhError) as err:
             ctx.estep_with_batch(ind, Fq, aq)
         assert err.value.status == 2
+
+
+def test_iteration_with_parameters_outside_the_optimiser_box(oracle):
+    """A caller may hand iter_EM parameters the optimiser's box does not contain (alpha > 10): the
+    reference runs forward/backward at the parameters as given (EM.cpp:151-185) and only setulb_ projects them
+    for the optimiser.  The fused E-step / first-round path must step aside instead of refusing."""
+    N, S = 3, 2000
+    d, ctx = _setup(N, S, 23, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    with ctx:
+        F0 = np.array([0.3, 0.4, 0.2]); a0 = np.array([12.0, 0.2, 0.3])
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.2, F0, a0)
+        runner = nfh.EmRank(ctx, freq_est=1)
+        Fi, ai = F0.copy(), a0.copy()
+        lk, fr = runner.iteration(Fi, ai)
+        st, marg1, lk_o = oracle.estep(e, d.dist_mb, F0, a0)
+        np.testing.assert_allclose(lk, lk_o, rtol=LKL_RTOL)
+        assert (ai <= 10.0).all()                                      # the optimiser projected it
