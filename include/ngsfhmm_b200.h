@@ -109,6 +109,14 @@ int nfh_emission_refresh(nfh_ctx *ctx, int with_e0);
  * NFH_WIN_POST_SEND; ind_lkl_out[n_ind_owned]. */
 int nfh_estep(nfh_ctx *ctx, double *ind_lkl_out);
 
+/* Introspection of the work order nfh_estep uses inside its single launch (csrc/nfh_schedule.h): item
+ * `ticket` of the order for n_rows individuals x n_tiles tiles in waves of wave_rows individuals with
+ * `lookahead` early product items.  item_out = {phase (0 products, 1 posteriors), individual, tile}; returns the
+ * number of items.  Pure host function (no device needed): lets the tests prove that every item appears once
+ * and that no posterior item precedes a product item of its wave. */
+uint64_t nfh_estep_schedule_item(uint32_t n_rows, uint32_t n_tiles, uint32_t wave_rows, uint32_t lookahead,
+                                 uint64_t ticket, uint32_t item_out[3]);
+
 /* Replaces: lkl() (EM.cpp:449-464) for many (individual, F, alpha) points per
  * launch - the objective evaluations findmax_bfgs asks for (bfgs.cpp:108-121).
  * ind[] are local individual indices; requests for the same individual

@@ -30,6 +30,7 @@ EXPORTS = [
     "nfh_geno_posterior", "nfh_exchange_window", "nfh_peer_export", "nfh_peer_import", "nfh_peer_direct", "nfh_sync", "nfh_stream", "nfh_probe_fp64", "nfh_timing",
     "nfh_timing_read", "nfh_freq_passes", "nfh_host_register", "nfh_host_unregister", "nfh_estep_with_batch",
     "nfh_device_count", "nfh_peer_set", "nfh_window_copy_block", "nfh_window_read", "nfh_window_write",
+    "nfh_estep_schedule_item",
 ]
 
 

@@ -11,6 +11,7 @@
 #include "ngsfhmm_b200.h"
 #include "nfh_device.cuh"
 #include "nfh_kernels.h"
+#include "nfh_schedule.h"
 
 using namespace nfh;
 
@@ -44,6 +45,7 @@ struct nfh_ctx {
   double4 *chunk_prod = nullptr;
   TileProd *tile_prod = nullptr, *lkl_tile_prod = nullptr;
   double2 *fwd_carry = nullptr, *bwd_carry = nullptr;
+  EstepFusedState fused;
   LklGroup *groups = nullptr;
   double *neg_lkl = nullptr;
   unsigned char *vit_work = nullptr, *vit_maps = nullptr;
@@ -169,6 +171,16 @@ const char *nfh_build_info(void) { return "ngsfhmm_b200 sm_100a fp64 (no CPU fal
 
 uint64_t nfh_kernel_launches(const nfh_ctx *ctx) { return ctx->launches; }
 
+uint64_t nfh_estep_schedule_item(uint32_t n_rows, uint32_t n_tiles, uint32_t wave_rows, uint32_t lookahead,
+                                 uint64_t ticket, uint32_t item_out[3]) {
+  const EstepSchedule s = make_schedule(n_rows, n_tiles, wave_rows, lookahead);
+  if (ticket < s.total && item_out) {
+    const EstepItem it = decode_ticket(s, (uint32_t) ticket);
+    item_out[0] = it.apply; item_out[1] = it.row; item_out[2] = it.tile;
+  }
+  return s.total;
+}
+
 int nfh_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -240,6 +252,10 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   NFH_TRY(alloc((void **) &ctx->lkl_tile_prod, ctx->n_loc * kMaxPoints * ctx->n_tiles * sizeof(TileProd), false));
   NFH_TRY(alloc((void **) &ctx->fwd_carry, ctx->n_loc * ctx->n_tiles * sizeof(double2), false));
   NFH_TRY(alloc((void **) &ctx->bwd_carry, ctx->n_loc * ctx->n_tiles * sizeof(double2), false));
+  NFH_TRY(alloc((void **) &ctx->fused.d_ticket, sizeof(unsigned long long), true));
+  NFH_TRY(alloc((void **) &ctx->fused.d_row_done, ctx->n_loc * sizeof(unsigned long long), true));
+  NFH_TRY(alloc((void **) &ctx->fused.d_row_claim, ctx->n_loc * sizeof(unsigned), true));
+  NFH_TRY(alloc((void **) &ctx->fused.d_row_ready, ctx->n_loc * sizeof(unsigned), true));
   NFH_TRY(alloc((void **) &ctx->groups, ctx->n_loc * sizeof(LklGroup), false));
   NFH_TRY(alloc((void **) &ctx->neg_lkl, ctx->n_loc * kMaxPoints * sizeof(double), false));
   for (int g = 0; g < 3; g++) NFH_TRY(alloc((void **) &ctx->gl[g], plane_frq, true));
@@ -282,7 +298,8 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   void *dev[] = {ctx->dist_t, ctx->tile_dmax, ctx->tile_dsum, ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
                  ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
                  ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
-                 ctx->status, ctx->freq_passes, ctx->freq_acc, ctx->d_stage};
+                 ctx->status, ctx->freq_passes, ctx->freq_acc, ctx->d_stage, ctx->fused.d_ticket, ctx->fused.d_row_done,
+                 ctx->fused.d_row_claim, ctx->fused.d_row_ready};
   for (void *p : dev) if (p) cudaFree(p);
   for (int r = 0; r < kMaxRanks; r++) {
     if (r == ctx->rank) continue;
@@ -480,6 +497,7 @@ static EstepArgs estep_args(nfh_ctx *ctx) {
   a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
   a.site_block = ctx->site_block; a.n_tiles = ctx->n_tiles;
   a.sm_count = ctx->sm_count;
+  a.fused = &ctx->fused;
   return a;
 }
 

@@ -35,6 +35,17 @@ struct LklGroup {   // objective requests of one individual sharing one read of 
   int out[kMaxPoints];
 };
 
+// Device counters of the single-launch E-step (estep_fused) plus the host's record of how far they have run;
+// owned by the context, zeroed at creation and never reset.
+struct EstepFusedState {
+  unsigned long long *d_ticket = nullptr;     // [1]
+  unsigned long long *d_row_done = nullptr;   // [n_rows]
+  unsigned *d_row_claim = nullptr;            // [n_rows]
+  unsigned *d_row_ready = nullptr;            // [n_rows]
+  unsigned long long ticket_base = 0;
+  unsigned epoch = 0;
+};
+
 struct EstepArgs {
   const double *emis;        // emission ratio, blocked [n_ranks][n_rows][site_block]
   const double *dist;        // [n_ranks * site_block] Mb
@@ -52,6 +63,7 @@ struct EstepArgs {
   uint64_t n_rows, n_rows_valid, n_sites, site_block;
   uint32_t n_tiles;
   int sm_count;
+  EstepFusedState *fused;    // NULL: three-launch E-step
 };
 
 struct LklArgs {

@@ -211,13 +211,7 @@ lkl_finish(const TileProd *__restrict__ tile_prod, const LklGroup *__restrict__ 
   }
 }
 
-namespace v1 {
-void launch_lkl_batch_v1(const LklArgs &a, cudaStream_t st);
-}
-
 void launch_lkl_batch(const LklArgs &a, cudaStream_t st) {
-  static const bool use_v1 = getenv("NFH_ESTEP_V1") != nullptr;
-  if (use_v1) { v1::launch_lkl_batch_v1(a, st); return; }
   static bool done[64] = {false};     // the attribute belongs to the (function, device) pair
   int dev = 0;
   cudaGetDevice(&dev);

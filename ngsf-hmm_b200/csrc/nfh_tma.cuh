@@ -43,6 +43,33 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                : "memory");
 }
 
+// L2 eviction policies for bulk copies: evict_last keeps a tile that is read again soon (the second sweep of
+// the E-step), evict_first marks data that is touched once (its last read, the posterior written out).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_addr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_1d_hint(void *gmem_dst, const void *smem_src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+               "r"(smem_addr(smem_src)), "r"(bytes), "l"(policy)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 // 2-D tiled tensor copy global -> shared through a CUtensorMap (box of rows x columns, optional swizzle);
 // coordinates are element indices, innermost first.  SASS: UTMALDG.
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_map, int x, int y, uint64_t *bar) {

@@ -67,7 +67,7 @@ def main():
             for _ in range(args.reps):
                 ctx.estep_async()
             ms = ctx.timing_read(reset=True)["estep"][0] / args.reps
-            out = {"kernel": "estep", "v1": bool(os.environ.get("NFH_ESTEP_V1")), "n_ind": N, "n_sites": S,
+            out = {"kernel": "estep", "single_launch": os.environ.get("NFH_ESTEP_FUSED", "0") not in ("", "0"), "n_ind": N, "n_sites": S,
                    "alpha": alpha, "ms": ms, "gbs_at_24B": 24.0 * N * S / (ms * 1e-3) / 1e9,
                    "frac_of_hbm_peak": 24.0 * N * S / (ms * 1e-3) / 1e9 / peak, "lkl0": float(lk[0])}
             if args.lkl:

@@ -424,3 +424,29 @@ def test_iteration_with_parameters_outside_the_optimiser_box(oracle):
         st, marg1, lk_o = oracle.estep(e, d.dist_mb, F0, a0)
         np.testing.assert_allclose(lk, lk_o, rtol=LKL_RTOL)
         assert (ai <= 10.0).all()                                      # the optimiser projected it
+
+
+@pytest.mark.parametrize("wave_rows,lookahead", [(1, 0), (2, 3), (3, 1000), (100, 5)])
+def test_single_launch_estep_matches_three_launch_path_and_oracle(oracle, monkeypatch, wave_rows, lookahead):
+    """nfh_estep's single-launch kernel (csrc/nfh_schedule.h) for several wave shapes, against the three-launch
+    path (NFH_ESTEP_FUSED=0) and the oracle: 7 individuals x 30,000 sites = 8 tiles each, parameters per
+    individual, a chromosome start in the middle; repeated calls reuse the never-reset device counters."""
+    N, S = 7, 30000
+    d, ctx = _setup(N, S, 21, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    with ctx:
+        d.dist_mb[[0, 17000]] = np.inf
+        rng = np.random.default_rng(4)
+        F0 = rng.uniform(0.01, 0.6, N); a0 = rng.uniform(0.005, 2.0, N)
+        gl_ind, freq, F, a, e = _prepare(oracle, d, ctx, 0.2, F0, a0)
+        monkeypatch.setenv("NFH_ESTEP_FUSED", "0")
+        lk3 = ctx.estep(); post3 = ctx.get_posterior()
+        monkeypatch.setenv("NFH_ESTEP_FUSED", "1")
+        monkeypatch.setenv("NFH_ESTEP_WAVE_ROWS", str(wave_rows))
+        monkeypatch.setenv("NFH_ESTEP_LOOKAHEAD", str(lookahead))
+        for rep in range(3):
+            lk1 = ctx.estep(); post1 = ctx.get_posterior()
+            np.testing.assert_allclose(lk1, lk3, rtol=1e-12, atol=0)
+            assert np.abs(post1 - post3).max() < 1e-11
+        st, marg1, lk_o = oracle.estep(e, d.dist_mb, F, a)
+        np.testing.assert_allclose(lk1, lk_o, rtol=LKL_RTOL, atol=0)
+        _posterior_check(post1, marg1)
