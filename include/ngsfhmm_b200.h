@@ -169,7 +169,10 @@ int nfh_exchange_window(nfh_ctx *ctx, int window, void **dev_ptr, uint64_t *byte
  *   - nfh_freq_update / nfh_emission_refresh write every emission ratio straight into the
  *     recursion-side window of the rank that owns the individual,
  * so no all-to-all is needed; the caller only has to order the stages across ranks (a 1-element
- * all-reduce on nfh_stream() before nfh_freq_update, and the all-reduce of NFH_WIN_LOGE0_SUM after it). */
+ * all-reduce on nfh_stream() before nfh_freq_update, and the all-reduce of NFH_WIN_LOGE0_SUM after it).
+ * enable = 2 keeps the posteriors of nfh_estep in the local NFH_WIN_POST_SEND and only sends the emission ratios
+ * direct: for runs whose frequencies are fixed (--freq_est 0, EM.cpp:224 skips the site loop), where nothing on the
+ * frequency side reads the posteriors and 8 bytes per individual-site would cross NVLink for nothing. */
 int nfh_peer_export(nfh_ctx *ctx, int window, unsigned char handle[64]);
 int nfh_peer_import(nfh_ctx *ctx, int window, int peer_rank, const unsigned char handle[64]);
 int nfh_peer_direct(nfh_ctx *ctx, int enable);

@@ -63,7 +63,9 @@ struct nfh_ctx {
   // peer windows (CUDA IPC), see nfh_peer_*
   double *peer_post[kMaxRanks] = {nullptr}, *peer_emis[kMaxRanks] = {nullptr};
   bool peer_post_ipc[kMaxRanks] = {false}, peer_emis_ipc[kMaxRanks] = {false};   // mapped by cudaIpcOpenMemHandle (to be closed)
-  bool peer_direct = false;
+  bool peer_direct = false;        // emission ratios go straight to the owners of the individuals
+  bool peer_post_direct = false;   // posterior tiles go straight to the owners of the site blocks
+  bool post_in_peers = false;      // where the last E-step put them (nfh_get_posterior reads there)
 
   int *status = nullptr;
   // pinned host scratch
@@ -491,7 +493,8 @@ static EstepArgs estep_args(nfh_ctx *ctx) {
   a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
   a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
   a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;
-  a.post_peers.direct = ctx->peer_direct ? 1 : 0;
+  a.post_peers.direct = ctx->peer_post_direct ? 1 : 0;
+  ctx->post_in_peers = ctx->peer_post_direct;
   a.post_peers.rank = ctx->rank; a.post_peers.n_loc = ctx->n_loc;
   for (int r = 0; r < kMaxRanks; r++) a.post_peers.base[r] = ctx->peer_post[r];
   a.n_rows = ctx->n_loc; a.n_rows_valid = ctx->n_owned; a.n_sites = ctx->n_sites;
@@ -661,7 +664,7 @@ int nfh_get_posterior(nfh_ctx *ctx, double *marg1_out) {
     if (s0 >= ctx->n_sites) break;
     const uint64_t w = std::min(ctx->site_block, ctx->n_sites - s0);
     // fused exchange: the E-step stored block b straight into rank b's frequency-side window (source block = me)
-    const double *src = ctx->peer_direct ? ctx->peer_post[b] + (size_t) ctx->rank * ctx->n_loc * ctx->site_block
+    const double *src = ctx->post_in_peers ? ctx->peer_post[b] + (size_t) ctx->rank * ctx->n_loc * ctx->site_block
                                          : ctx->post_send + (size_t) b * ctx->n_loc * ctx->site_block;
     NFH_CUDA(cudaMemcpy2DAsync(marg1_out + s0, ctx->n_sites * sizeof(double), src, ctx->site_block * sizeof(double),
                                w * sizeof(double), ctx->n_owned, cudaMemcpyDeviceToHost, ctx->stream));
@@ -813,6 +816,7 @@ int nfh_peer_direct(nfh_ctx *ctx, int enable) {
         return fail(ctx, NFH_ERR_ARG, "nfh_peer_direct: import the POST_RECV and EMIS_RECV windows of every rank first");
   }
   ctx->peer_direct = enable != 0;
+  ctx->peer_post_direct = enable == 1;      // enable == 2: emission ratios only
   return NFH_OK;
 }
 

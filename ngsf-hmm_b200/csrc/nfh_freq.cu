@@ -392,7 +392,13 @@ freq_emission_warp(const __grid_constant__ FreqArgs A, unsigned n_site_tiles) {
 // deliver beside the FP64 work.
 // ---------------------------------------------------------------------------
 constexpr int kHybridRegK = 12;      // 9 gave the same time: the compiler fills 255 registers either way
-constexpr int kHybridMaxKS = 14;
+constexpr int kHybridMaxKS = 14;     // with kHybridRegK register individuals: n_ind <= 832
+// Beyond that (the frequency side of 8 ranks x 125 individuals sees 1,000): 13 or 14 register individuals and up to
+// 18 in shared memory (110,592 bytes per CTA, still two CTAs per SM) reach n_ind = 1,024.  The team kernel that took
+// these sizes before gives every CTA ONE site, so that a CTA uses 8 of the 32 bytes of every sector it fetches and
+// slows down with the row length (1.71 ps per individual-pass at 50,000 sites per row, 2.21 at 1.25M, 2.76 with peer
+// stores on 8 GPUs); here the four warps of a CTA work on four neighbouring sites.
+constexpr int kHybridMaxKSWide = 18;
 
 // partial sums of the KS shared-memory individuals of this lane (same algebra as pass_sums)
 template <int KS>
@@ -425,10 +431,10 @@ __device__ __forceinline__ void hybrid_sums(const double *__restrict__ coef, dou
   }
 }
 
-template <int G, int KS>
+template <int G, int KS, int KR>
 __global__ void __launch_bounds__(kFreqThreads, 2)
 freq_emission_hybrid(FreqArgs A, unsigned n_site_tiles) {
-  constexpr int KR = kHybridRegK, K = KR + KS;
+  constexpr int K = KR + KS;
   constexpr int kSitesPerWarp = 32 / G;
   constexpr int kSitesPerCta = kSitesPerWarp * (kFreqThreads / 32);
   constexpr int kWarps = kFreqThreads / 32;
@@ -821,9 +827,16 @@ __global__ void __launch_bounds__(256) fp64_probe(double *sink, int iters) {
 
 // ---------------------------------------------------------------------------
 
-// Choose lanes-per-site G and individuals-per-lane K <= 16: the fewest padded
-// slots wins (measured at 100 individuals: G=8,K=13 12.6 ms vs G=16,K=7 13.7 ms
-// per million sites - padding costs more than the extra occupancy gains).
+// Choose lanes-per-site G and individuals-per-lane K <= 16 by a measured cost model (profiles/r02/freq_shapes.md,
+// B200, picoseconds per individual SLOT and pass): 0.92 for the slot itself + a per-pass tail that is paid per lane
+// group and grows with the group (shuffle levels) and is shared by the K individuals of a lane + a spill penalty
+// beyond K = 13.  Padded slots cost like real ones.  Examples: 100 -> (8,13), 125 -> (16,8), 200 -> (16,13),
+// 400 -> (32,13); the round-1 rule (fewest padded slots, widest group on ties) took (32,4) for 125: 1.54 vs 1.09 ps.
+static double shape_cost(int g, int k) {
+  const double tail = g == 4 ? 0.2 : g == 8 ? 0.364 : g == 16 ? 1.144 : 2.18;
+  return (double) g * k * (0.922 + tail / k + (k > 13 ? 0.06 * (k - 13) : 0.0));
+}
+
 static bool pick_shape(uint64_t n_ind, int &G, int &K) {
   if (const char *force = getenv("NFH_FREQ_G")) {   // tuning override: lanes per site
     const int g = atoi(force);
@@ -831,25 +844,27 @@ static bool pick_shape(uint64_t n_ind, int &G, int &K) {
     if ((g == 4 || g == 8 || g == 16 || g == 32) && k >= 1 && k <= kMaxK) { G = g; K = k; return true; }
   }
   int best_g = 0, best_k = 0;
-  uint64_t best_slots = ~0ull;
+  double best = 0.0;
   for (int g = 4; g <= 32; g <<= 1) {
     const int k = (int) ((n_ind + g - 1) / g);
     if (k < 1 || k > kMaxK) continue;
-    const uint64_t slots = (uint64_t) g * k;
-    if (slots <= best_slots) { best_slots = slots; best_g = g; best_k = k; }
+    const double c = shape_cost(g, k);
+    if (!best_g || c < best) { best = c; best_g = g; best_k = k; }
   }
   G = best_g; K = best_k;
   return best_g != 0;
 }
 
-// Hybrid variant (G = 32): 512 < n_ind <= 32 (kHybridRegK + kHybridMaxKS) = 832, where it beats two-warp teams
+// Hybrid variant (G = 32): 512 < n_ind <= 1,024; up to 832 it beats two-warp teams
 // (13.9 vs 15.1 ms at 800 individuals x 125,000 sites).  With fewer individuals the register-only shapes with
 // their tile prefetch are faster (200: 10.4 vs 12.6 ms, 400: 11.4 vs 13.4 ms).
-static bool pick_hybrid_shape(uint64_t n_ind, int &G, int &KS) {
+static bool pick_hybrid_shape(uint64_t n_ind, int &G, int &KS, int &KR) {
   if (getenv("NFH_FREQ_NO_HYBRID")) return false;
   const int k = (int) ((n_ind + 31) / 32);
-  if (n_ind <= 512 || k > kHybridRegK + kHybridMaxKS) return false;
-  G = 32; KS = k - kHybridRegK;
+  if (n_ind <= 512 || k > 14 + kHybridMaxKSWide) return false;
+  G = 32;
+  KR = k <= kHybridRegK + kHybridMaxKS ? kHybridRegK : (k <= 13 + kHybridMaxKSWide ? 13 : 14);
+  KS = k - KR;
   return true;
 }
 
@@ -874,8 +889,8 @@ unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   int G, K, W;
   unsigned per_cta = 0;
   unsigned ctas_per_sm = 4;
-  int KS;
-  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = 2; }
+  int KS, KR;
+  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS, KR)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = 2; }
   else if (pick_shape(a.n_ind, G, K)) { per_cta = (32 / G) * (kFreqThreads / 32); ctas_per_sm = freq_occupancy(K); }
   else if (pick_team_shape(a.n_ind, W, K)) per_cta = ((W <= 4 ? 128 : 256) / 32) / W;
   if (per_cta) {
@@ -988,32 +1003,31 @@ static bool dispatch_team_k(int K, const FreqArgs &a, unsigned grid, cudaStream_
   }
 }
 
-template <int G, int KS>
+template <int G, int KS, int KR>
 static void launch_hybrid_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
   const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t smem = (size_t) KS * 6 * kFreqThreads * sizeof(double);
   // per launch: the attribute belongs to the current device, and a process may drive several
-  cudaFuncSetAttribute(freq_emission_hybrid<G, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-  freq_emission_hybrid<G, KS><<<grid, kFreqThreads, smem, st>>>(a, tiles);
+  cudaFuncSetAttribute(freq_emission_hybrid<G, KS, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  freq_emission_hybrid<G, KS, KR><<<grid, kFreqThreads, smem, st>>>(a, tiles);
 }
 
 template <int G>
-static bool dispatch_hybrid(int KS, const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  switch (KS) {
-#define NFH_CASE(k) case k: launch_hybrid_variant<G, k>(a, grid, st); return true;
-    NFH_CASE(5) NFH_CASE(6) NFH_CASE(7) NFH_CASE(8) NFH_CASE(9) NFH_CASE(10)
-    NFH_CASE(11) NFH_CASE(12) NFH_CASE(13) NFH_CASE(14)
+static bool dispatch_hybrid(int KS, int KR, const FreqArgs &a, unsigned grid, cudaStream_t st) {
+#define NFH_CASE(ks, kr) if (KS == ks && KR == kr) { launch_hybrid_variant<G, ks, kr>(a, grid, st); return true; }
+  NFH_CASE(5, 12) NFH_CASE(6, 12) NFH_CASE(7, 12) NFH_CASE(8, 12) NFH_CASE(9, 12) NFH_CASE(10, 12)
+  NFH_CASE(11, 12) NFH_CASE(12, 12) NFH_CASE(13, 12) NFH_CASE(14, 12)
+  NFH_CASE(14, 13) NFH_CASE(15, 13) NFH_CASE(16, 13) NFH_CASE(17, 13) NFH_CASE(18, 13) NFH_CASE(18, 14)
 #undef NFH_CASE
-    default: return false;
-  }
+  return false;
 }
 
 int launch_freq_emission(const FreqArgs &a, unsigned grid, cudaStream_t st) {
-  int G, K, W, KS;
-  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS)) {
+  int G, K, W, KS, KR;
+  if (a.acc_scratch && pick_hybrid_shape(a.n_ind, G, KS, KR)) {
     bool ok = false;
-    if (G == 32) ok = dispatch_hybrid<32>(KS, a, grid, st);
+    if (G == 32) ok = dispatch_hybrid<32>(KS, KR, a, grid, st);
     if (ok) return 1;
   }
   if (pick_shape(a.n_ind, G, K)) {

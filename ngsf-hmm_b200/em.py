@@ -149,7 +149,8 @@ class EmRank:
             dist.all_gather_object(handles, mine, group=self.group)
             for r, h in enumerate(handles):
                 self.ctx.peer_import(which, r, h)
-        self.ctx.peer_direct(True)
+        # fixed frequencies (--freq_est 0): nothing on the frequency side reads the posteriors - keep them local
+        self.ctx.peer_direct(1 if self.freq_est else 2)
         self.direct = True
         self._token = torch.zeros(1, device=f"cuda:{torch.cuda.current_device()}")
         return True

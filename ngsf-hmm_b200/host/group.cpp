@@ -176,6 +176,9 @@ int nfh_group_freq_init(nfh_group *g, double *freq_out) {
 int nfh_group_em_iteration(nfh_group *g, double *indF, double *alpha, int F_fixed, int alpha_fixed, int freq_est,
                            double *ind_lkl_out, double *freq_out, uint64_t stats_out[3]) {
   std::vector<uint64_t> st(3 * (size_t) g->n_ranks, 0);
+  // fixed frequencies: nobody on the frequency side reads the posteriors, they stay with their individuals
+  if (g->direct)
+    for (nfh_ctx *c : g->ctx) nfh_peer_direct(c, freq_est ? 1 : 2);
   // stage 1: E-step + F / alpha update on the owners of the individuals (EM.cpp:151-205)
   int rc = on_all_ranks(g, [&](int r) {
     nfh_ctx *c = g->ctx[r];

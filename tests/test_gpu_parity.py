@@ -125,10 +125,11 @@ def test_freq_update_matches_oracle(oracle, N, S, seed):
         _posterior_check(ctx.get_posterior(), marg2)
 
 
-@pytest.mark.parametrize("N,S,no_hybrid", [(150, 300, 0), (450, 64, 0), (600, 48, 0), (820, 40, 0), (600, 48, 1),
-                                           (1100, 40, 0), (4200, 12, 0)],
-                         ids=["warp-G16", "warp-G32-global-acc", "hybrid-K19", "hybrid-K26", "team-W2", "team-W4",
-                              "stream"])
+@pytest.mark.parametrize("N,S,no_hybrid", [(150, 300, 0), (125, 300, 0), (450, 64, 0), (600, 48, 0), (820, 40, 0),
+                                           (900, 40, 0), (990, 40, 0), (1000, 40, 0), (600, 48, 1), (1100, 40, 0),
+                                           (4200, 12, 0)],
+                         ids=["warp-G16", "warp-G16-K8", "warp-G32-global-acc", "hybrid-K19", "hybrid-K26",
+                              "hybrid-13+16", "hybrid-13+18", "hybrid-14+18", "team-W2", "team-W4", "stream"])
 def test_freq_update_large_n_variants(oracle, monkeypatch, N, S, no_hybrid):
     """More individuals than one 8-lane group holds: wider lane groups (tile prefetch with accumulators in
     shared memory or global scratch), the register + shared-memory hybrid, teams of warps, the streaming path."""
