@@ -58,10 +58,12 @@ __device__ __forceinline__ double split_exponent(double x, int &e) {
 __device__ __forceinline__ IndCoef make_coef(double L0, double L1, double L2, double F) {
   IndCoef k;
   double c1 = 2.0 * L1 * (1.0 - F);
-  // A heterozygote call (L0 = L2 = 0) at a site whose IBD posterior was
-  // clamped to exactly 1 has zero weight for every genotype; the reference's
-  // log-space arithmetic (-1e15 stands for log 0) resolves this to "certainly
-  // heterozygous".  Keep a vanishing het weight so the ratio is 1, not 0/0.
+  // A heterozygote call (L0 = L2 = 0) with an IBD posterior of exactly 1 has zero weight for every genotype.
+  // INTENTIONAL DIVERGENCE, unreachable through the EM: a hard het call makes the emission ratio e1/e0 zero,
+  // which forces the posterior to 0, so only a caller that writes its own posterior window can get here.  The
+  // reference's log-space code (-1e15 standing for log 0, quantised at 0.125 at that magnitude) then yields
+  // genotype weights roughly proportional to (1-f, 1, f) (num += (1+f)/2, den += 1.5); here the individual is
+  // taken as certainly heterozygous (num += 1, den += 2): keep a vanishing het weight so the ratio is 1, not 0/0.
   if (L0 == 0.0 && L2 == 0.0 && F == 1.0) c1 = 1e-30;   // products of four S must stay normal
   k.g = 2.0 - F;
   k.a0 = L0; k.a2 = L2;

@@ -223,3 +223,33 @@ def test_n_gpus_equals_one_gpu(tmp_path, n_gpus):
     _, p1, m1 = _parse_ibd(str(tmp_path / "one.ibd"), N)
     _, pn, mn = _parse_ibd(str(tmp_path / "ours.ibd"), N)
     assert (p1 != pn).sum() == 0 and np.abs(m1 - mn).max() <= 1.1e-5
+
+
+PATCHED = os.path.join(ROOT, "oracle", "_ref", "ngsF-HMM_b200patch")
+
+
+@pytest.mark.parametrize("fixed", [False, True], ids=["free-parameters", "fixed-parameters"])
+def test_reference_patched_as_in_integration_md(tmp_path, fixed):
+    """INTEGRATION.md section B exercised: the reference's own objects (main, argument parsing, readers, EM()'s
+    iteration control, print_iter) with iter_EM and viterbi overridden by oracle/ref_patch/b200_patch.cpp, which
+    calls the C ABI (oracle/Makefile, target `patched`).  Its output files against the unmodified reference's."""
+    if not os.path.exists(PATCHED):
+        pytest.skip("oracle/_ref/ngsF-HMM_b200patch not built (needs /root/reference at build time)")
+    N, S = 7, 2500
+    d = sim.simulate(N, S, seed=2024, freq=(0.1, 0.5), indF=(0.1, 0.6), alpha=0.02, depth=2.0)
+    sim.write_beagle_gz(str(tmp_path / "in.beagle.gz"), d.log_gl, d.pos_bp)
+    sim.write_pos(str(tmp_path / "in.pos"), d.pos_bp)
+    common = ["--geno", "in.beagle.gz", "--lkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos",
+              "--min_iters", "3", "--max_iters", "4", "--seed", "1", "--verbose", "1", "--n_threads", "4"]
+    if fixed:
+        np.savetxt(str(tmp_path / "freq.txt"), np.clip(d.true_freq, 0.01, 0.49), fmt="%.6f")
+        with open(str(tmp_path / "indF.txt"), "w") as fh:
+            for i in range(N):
+                fh.write(f"{max(d.true_F[i], 1e-3):.6f}\t{d.true_alpha[i]:.6f}\n")
+        common += ["--freq", "freq.txt", "--freq_est", "0", "--indF", "indF.txt", "--indF_fixed", "--alpha_fixed"]
+    else:
+        common += ["--freq", "0.1", "--indF", "0.1,0.2", "--freq_est", "1"]
+    _run(REF, common + ["--out", "ref"], str(tmp_path))
+    out = _run(PATCHED, common + ["--out", "ours"], str(tmp_path))
+    assert "Iteration 3:" in out and "Final logLkl" in out
+    _compare(tmp_path, N, S, f_tol=1e-9 if fixed else 2e-5)
