@@ -293,7 +293,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_ranks = world
     N_total, S = args.n_ind * n_ranks, args.n_sites
-    direct = world > 1 and os.environ.get("NFH_PEER_DIRECT", "1") != "0"
+    # exchange between the recursion side and the frequency side: kernels storing into peer windows (fused) or NCCL
+    # all-to-alls.  Measured on 8 B200 (profiles/r02): with 100 MB per peer block (configs[1]) the fused stores win,
+    # with 1.25 GB per peer block (configs[2]) the all-to-alls do (314 vs 351 ms per EM iteration: the posterior
+    # exchange hides behind the BFGS rounds and the E-step is not NVLink-bound).  NFH_PEER_DIRECT=0/1 overrides.
+    peer_block_bytes = args.n_ind * (-(-S // (n_ranks * 4224)) * 4224) * 8 if world > 1 else 0
+    env_direct = os.environ.get("NFH_PEER_DIRECT", "")
+    direct = world > 1 and (env_direct != "0" if env_direct else (args.fixed or peer_block_bytes <= 512 << 20))
 
     def barrier():
         if world > 1:

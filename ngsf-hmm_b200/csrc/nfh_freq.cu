@@ -20,6 +20,8 @@
 //   num += (w1 + w2 (2-F)) / (w0+w1+w2)
 //   den += (2 w1 + (w0+w2)(2-F)) / (w0+w1+w2)
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "nfh_device.cuh"
 #include "nfh_kernels.h"
@@ -903,6 +905,19 @@ unsigned freq_grid_size(const FreqArgs &a, int sm_count) {
   return 64;   // chunks of loge0_rowsum
 }
 
+// The dynamic shared-memory limit belongs to the (kernel, device) pair: set it once for each, not per launch.
+static void smem_limit_once(const void *kernel, int bytes) {
+  static std::unordered_map<const void *, unsigned long long> done;   // kernel -> bit per device
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  unsigned long long &mask = done[kernel];
+  if (dev >= 0 && dev < 64 && (mask >> dev & 1ull)) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+}
+
 template <int G, int K>
 static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t st) {
   const unsigned per_cta = FreqTile<G>::kSitesPerCta;
@@ -912,9 +927,8 @@ static void launch_warp_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   const size_t smem_cap = (size_t) 228 * 1024 / freq_occupancy(K) - 1024 - 256;
   const size_t bufs = 2 * FreqTile<G>::tile_bytes(a.n_ind) + FreqTile<G>::kAlign;   // + alignment slack
   const bool want = a.use_maps && getenv("NFH_FREQ_NO_PREFETCH") == nullptr;
-  // per launch: the attribute belongs to the current device, and a process may drive several
-  cudaFuncSetAttribute(freq_emission_warp<G, K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
-  cudaFuncSetAttribute(freq_emission_warp<G, K, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_cap);
+  smem_limit_once((const void *) freq_emission_warp<G, K, 1>, (int) smem_cap);
+  smem_limit_once((const void *) freq_emission_warp<G, K, 2>, (int) smem_cap);
   if (want && acc + bufs <= smem_cap) freq_emission_warp<G, K, 1><<<grid, kFreqThreads, acc + bufs, st>>>(a, tiles);
   else if (want && a.acc_scratch && bufs <= smem_cap) freq_emission_warp<G, K, 2><<<grid, kFreqThreads, bufs, st>>>(a, tiles);
   else freq_emission_warp<G, K, 0><<<grid, kFreqThreads, acc, st>>>(a, tiles);
@@ -976,8 +990,7 @@ static void launch_team_variant(const FreqArgs &a, unsigned grid, cudaStream_t s
   constexpr int kTeams = (kThreads / 32) / W;
   const unsigned tiles = (unsigned) ((a.sites_owned + kTeams - 1) / kTeams);
   size_t smem = (size_t) kTeams * a.n_ind_pad * (sizeof(double) + sizeof(int));
-  // per launch: the attribute belongs to the current device, and a process may drive several
-  cudaFuncSetAttribute(freq_emission_team<W, K, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  smem_limit_once((const void *) freq_emission_team<W, K, kThreads>, 160 * 1024);
   freq_emission_team<W, K, kThreads><<<grid, kThreads, smem, st>>>(a, tiles);
 }
 
@@ -1010,8 +1023,7 @@ static void launch_hybrid_variant(const FreqArgs &a, unsigned grid, cudaStream_t
   const unsigned per_cta = (32 / G) * (kFreqThreads / 32);
   const unsigned tiles = (unsigned) ((a.sites_owned + per_cta - 1) / per_cta);
   const size_t smem = (size_t) KS * 6 * kFreqThreads * sizeof(double);
-  // per launch: the attribute belongs to the current device, and a process may drive several
-  cudaFuncSetAttribute(freq_emission_hybrid<G, KS, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  smem_limit_once((const void *) freq_emission_hybrid<G, KS, KR>, (int) smem);
   freq_emission_hybrid<G, KS, KR><<<grid, kFreqThreads, smem, st>>>(a, tiles);
 }
 
