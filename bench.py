@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--n_sites", type=int, default=None)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_parity_check", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="multi-rank: per-phase stream times of every rank (extra untimed leg)")
     ap.add_argument("--cpu_sites", type=int, default=20000, help="sites of the bounded CPU sample (reference arm)")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
@@ -293,13 +294,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n_ranks = world
     N_total, S = args.n_ind * n_ranks, args.n_sites
-    # exchange between the recursion side and the frequency side: kernels storing into peer windows (fused) or NCCL
-    # all-to-alls.  Measured on 8 B200 (profiles/r02): with 100 MB per peer block (configs[1]) the fused stores win,
-    # with 1.25 GB per peer block (configs[2]) the all-to-alls do (314 vs 351 ms per EM iteration: the posterior
-    # exchange hides behind the BFGS rounds and the E-step is not NVLink-bound).  NFH_PEER_DIRECT=0/1 overrides.
-    peer_block_bytes = args.n_ind * (-(-S // (n_ranks * 4224)) * 4224) * 8 if world > 1 else 0
-    env_direct = os.environ.get("NFH_PEER_DIRECT", "")
-    direct = world > 1 and (env_direct != "0" if env_direct else (args.fixed or peer_block_bytes <= 512 << 20))
+    # exchange between the recursion side and the frequency side.  Measured on 8 B200 (profiles/r02):
+    #   all-to-alls both ways ("nccl", the posterior one behind the BFGS rounds): 20.5 ms per EM iteration of configs[1]
+    #     at 8 GPUs, 314 ms of configs[2];
+    #   kernels storing into peer windows ("direct"): 21.8 / 351 ms - the posterior tiles of all ranks hit NVLink in
+    #     the same millisecond and the E-step + BFGS phase of most ranks stretches from 4.1 to 6.3 ms;
+    #   "mixed" (posteriors by all-to-all, emission ratios by peer stores from the frequency kernel): best at 2 and 4
+    #     GPUs (15.6 / 16.8 ms against 16.4 / - ), not yet run at 8 (its first 8-rank run hung in the self-check on the
+    #     ranks that own no individual of the 11; fixed in bfgs_update_lockstep and covered by a CPU test since, but
+    #     there was no GPU time left to repeat it) - opt-in until it has;
+    #   fixed frequencies: nothing to exchange per iteration ("direct" = emission refresh by peer stores, once).
+    # NFH_EXCHANGE=direct|mixed|nccl overrides (NFH_PEER_DIRECT=0/1 = nccl/direct is still honoured).
+    mode = os.environ.get("NFH_EXCHANGE", "")
+    if not mode and os.environ.get("NFH_PEER_DIRECT", "") in ("0", "1"):
+        mode = "direct" if os.environ["NFH_PEER_DIRECT"] == "1" else "nccl"
+    if not mode:
+        mode = "direct" if args.fixed else "nccl"
+    if world == 1:
+        mode = "none"
+    direct = {"direct": True, "mixed": "mixed", "nccl": False, "none": False}[mode]
 
     def barrier():
         if world > 1:
@@ -331,8 +344,10 @@ def main():
     exchange = "none (1 rank)"
     if world > 1:
         if direct:
-            runner.enable_peer_direct()
-            exchange = "fused: kernels store into peer windows over NVLink (CUDA IPC)"
+            runner.enable_peer_direct(posteriors=direct != "mixed")
+            exchange = ("fused: kernels store into peer windows over NVLink (CUDA IPC)" if direct is True else
+                        "mixed: posteriors by NCCL all-to-all behind the BFGS rounds, emission ratios stored into peer "
+                        "windows by the frequency kernel")
         else:
             exchange = "NCCL all-to-all"
     n_own = ctx.n_ind_owned
@@ -356,11 +371,19 @@ def main():
         gpu_uuid = None
     sampler = ClockSampler(local_rank, gpu_uuid)
 
+    # ---- settling pass (untimed, discarded): the W + K iterations the legs below repeat, run once beforehand, so that
+    #      one-off costs of a fresh process - lazily loaded kernel variants (the objective kernel has one per point
+    #      layout), NCCL connections, the page-locked frequency buffer - do not land in the first timed leg (on 2 GPUs
+    #      the first leg was 1.3 ms per step slower than the identical later ones)
+    F, a = reset_state()
+    for _ in range(args.warmup + args.steps):
+        runner.iteration(F, a, want_freq=bool(freq_est))
+
     # ---- device-timed leg: reset, W warm-up iterations, then K EM iterations, state resident in HBM
     F, a = reset_state()
     for _ in range(args.warmup):
-        runner.iteration(F, a, want_freq=bool(freq_est))    # also page-locks the frequency download buffer (one-off)
-    ctx.timing(True)
+        runner.iteration(F, a, want_freq=bool(freq_est))
+    ctx.timing(os.environ.get("NFH_BENCH_NO_FAMILY_TIMING", "") != "1")
     ctx.timing_read(reset=True)
     ctx.freq_passes(reset=True)
     launches0 = ctx.kernel_launches
@@ -397,6 +420,30 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     h2d = 2 * n_own * 8 + (evals / max(args.steps, 1)) * (4 + 8 + 8)
     d2h = n_own * 8 + (ctx.sites_owned * 8 if freq_est else 0) + (evals / max(args.steps, 1)) * 8
+
+    # ---- optional: where a multi-rank step goes, rank by rank (separate untimed leg, CUDA events between the phases)
+    rank_trace = None
+    if args.trace and world > 1 and freq_est:
+        F, a = reset_state()
+        for _ in range(args.warmup):
+            runner.iteration(F, a, want_freq=False)
+        runner.trace = []
+        r0 = runner.total_rounds
+        barrier()
+        tt0 = time.perf_counter()
+        for _ in range(args.steps):
+            runner.iteration(F, a, want_freq=False)
+        barrier()
+        trace_ms = (time.perf_counter() - tt0) * 1e3 / args.steps
+        tsum = runner.trace_summary()
+        runner.trace = None
+        mine = torch.tensor([tsum["estep_bfgs"], tsum["wait_ranks"], tsum["freq"], tsum["exchange_back"],
+                             (runner.total_rounds - r0) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_trace = {"wall_ms_per_step_of_this_leg": trace_ms,
+                      "columns": ["estep_bfgs_ms", "wait_ranks_ms", "freq_ms", "exchange_back_ms", "bfgs_rounds"],
+                      "per_rank": [[round(float(x), 3) for x in t] for t in allr]}
 
     # ---- the E-step on its own (products + carries + apply): inside a free-parameter EM iteration its forward
     #      products ride on the first objective round, so the per-step "estep" time covers carries + apply only
@@ -456,7 +503,8 @@ def main():
         roofs = {"estep": roof_estep}
         if not args.fixed:
             passes_per_site = site_passes / max(ctx.sites_owned * args.steps, 1)
-            freq_tf = FREQ_FLOPS_PER_IND_PASS * passes_per_site * freq_units / (per_step["freq"] * 1e-3) / 1e12
+            freq_tf = (FREQ_FLOPS_PER_IND_PASS * passes_per_site * freq_units / (per_step["freq"] * 1e-3) / 1e12
+                       if per_step["freq"] > 0 else 0.0)
             evals_step = evals / args.steps
             lkl_flops = (LKL_FLOPS_PER_IND_SITE_POINT + 0.6 * EXP_FLOPS) * evals_step * S
             lkl_tf = lkl_flops / (per_step["lkl_batch"] * 1e-3) / 1e12 if per_step["lkl_batch"] > 0 else 0.0
@@ -491,17 +539,18 @@ def main():
                              f"exceed the 126 MB L2",
                        "parallelism": f"individuals sharded x{world}, sites sharded x{world} for the freq stage",
                        "exchange": exchange,
-                       "legs": "device-timed and end-to-end legs both start from reset state + the same warm-up"},
+                       "legs": "device-timed and end-to-end legs both start from reset state + the same warm-up, after one "
+                               "discarded pass over the same iterations"},
             "roofline": roofs[dominant], "roofline_estep": roof_estep,
             "kernel_ms_per_step": per_step,
             "fp64_peak": fp64_note,
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
                     "note": "GL upload and final posterior/path download are one-off per run, see e2e_full_run"},
-            "e2e_full_run": {"seconds": t_full, "iterations": 2 * (args.steps + args.warmup),
-                             "covers": "context creation, synthetic GL generation on the GPU, nfh_upload_gl, both "
-                                       "timed legs with their warm-ups, emission refresh with e0, Viterbi, path and "
-                                       "posterior download", "generate_s": t_gen, "gl_upload_s": t_upload,
+            "e2e_full_run": {"seconds": t_full, "iterations": 3 * (args.steps + args.warmup),
+                             "covers": "context creation, synthetic GL generation on the GPU, nfh_upload_gl, the settling "
+                                       "pass and both timed legs with their warm-ups, emission refresh with e0, Viterbi, "
+                                       "path and posterior download", "generate_s": t_gen, "gl_upload_s": t_upload,
                              "gl_bytes": gl_bytes, "final_refresh_viterbi_download_s": t_final_ms / 1e3},
             "viterbi": {"kernel_ms": vit_ms, "ind_sites_per_s": float(N_total) * S / (vit_ms * 1e-3) if vit_ms > 0 else None,
                         "refresh_with_e0_s": t2 - t1, "decode_and_path_download_s": t3 - t2,
@@ -515,6 +564,8 @@ def main():
             out["bfgs"] = {"objective_evals_per_step": evals / args.steps, "rounds_per_step": rounds / args.steps}
         if parity is not None:
             out["parity_check"] = parity
+        if rank_trace is not None:
+            out["rank_trace"] = rank_trace
         if not args.no_cpu_baseline:
             try:
                 out["cpu_baseline"] = reference_arm(args, as_cpu_baseline=True)

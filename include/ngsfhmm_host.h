@@ -34,6 +34,15 @@ int nfh_host_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
 int nfh_host_estep_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed,
                                int alpha_fixed, double *ind_lkl_out, uint64_t stats_out[3]);
 
+/* The same with a hook for multi-rank callers: posterior_ready(user) is called once, from the calling thread, as soon
+ * as the posteriors of this E-step are complete in NFH_WIN_POST_SEND - after the first optimiser round; the rounds
+ * that follow only read the emission window - so that their exchange to the frequency side (EM.cpp:224-271 needs
+ * every individual's posterior at a site) can run behind the rest of the optimisation. */
+typedef void (*nfh_stage_hook)(void *user);
+int nfh_host_estep_bfgs_update_hook(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed,
+                                    int alpha_fixed, double *ind_lkl_out, uint64_t stats_out[3],
+                                    nfh_stage_hook posterior_ready, void *user);
+
 /* Replaces iter_EM (EM.cpp:139-289) on one rank: E-step with the given
  * parameters, F/alpha update against the old emissions, frequency update +
  * emission refresh with the new posteriors.  indF/alpha in/out [n_ind_owned];

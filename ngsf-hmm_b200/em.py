@@ -20,6 +20,7 @@ from . import api
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _dp = C.POINTER(C.c_double)
+_HOOK = C.CFUNCTYPE(None, C.c_void_p)
 _hostlib = None
 
 
@@ -77,8 +78,11 @@ class EmRank:
         self._ext_stream = None
         self._side = None
         self._post_done = None
-        self.direct = False
+        self.direct = False           # posterior tiles AND emission ratios stored into peer windows by the kernels
+        self.mixed = False            # emission ratios by peer stores, posteriors by all-to-all behind the BFGS rounds
         self._token = None
+        self._hook = None
+        self.trace = None             # list of per-iteration CUDA-event tuples when tracing (bench.py --trace)
 
     # -- multi-rank plumbing ------------------------------------------------
     def _tensor(self, which):
@@ -136,13 +140,20 @@ class EmRank:
                 exchange_all_to_all(self._tensor(api.WIN_E0_SEND), self._tensor(api.WIN_E0_RECV), self.group)
             dist.all_reduce(self._tensor(api.WIN_LOGE0_SUM), group=self.group)
 
-    def enable_peer_direct(self):
+    def enable_peer_direct(self, posteriors=True):
         """Fused exchange: all-gather the CUDA IPC handles of every rank's receive windows and let the
-        E-step / frequency kernels store straight into the owner's window over NVLink."""
-        if self.ctx.n_ranks == 1:
-            return False
+        kernels store straight into them (nfh_peer_export / nfh_peer_import / nfh_peer_direct).
+
+        posteriors=False ("mixed"): only the emission ratios go by peer stores; the posteriors stay local
+        and travel by an all-to-all that is started as soon as the E-step is complete and runs behind the
+        remaining BFGS rounds.  On 8 GPUs the posterior tiles of all ranks cross NVLink in the same
+        millisecond when the kernels store them (E-step + BFGS phase 4.2-6.4 ms per rank against 4.0-4.3
+        with the all-to-all, profiles/r02/bench_r02t_*), while the emission ratios are spread over the 14 ms
+        of the frequency kernel, where peer stores beat a separate all-to-all (0.6 against 1.6 ms)."""
         import torch
         import torch.distributed as dist
+        if self.ctx.n_ranks == 1:
+            return False
         for which in (api.WIN_POST_RECV, api.WIN_EMIS_RECV):
             mine = self.ctx.peer_export(which)
             handles = [None] * self.ctx.n_ranks
@@ -150,8 +161,9 @@ class EmRank:
             for r, h in enumerate(handles):
                 self.ctx.peer_import(which, r, h)
         # fixed frequencies (--freq_est 0): nothing on the frequency side reads the posteriors - keep them local
-        self.ctx.peer_direct(1 if self.freq_est else 2)
-        self.direct = True
+        self.ctx.peer_direct(1 if (self.freq_est and posteriors) else 2)
+        self.direct = bool(posteriors or not self.freq_est)
+        self.mixed = not self.direct
         self._token = torch.zeros(1, device=f"cuda:{torch.cuda.current_device()}")
         return True
 
@@ -170,7 +182,7 @@ class EmRank:
     # -- iteration ----------------------------------------------------------
     def refresh_emissions(self, with_e0=False):
         self.ctx.emission_refresh(with_e0)
-        if self.direct:
+        if self.direct or self.mixed:
             # ratios were stored into the owners' windows by the kernel; e0 (Viterbi only) still travels by NCCL
             if with_e0:
                 with self._stream_ctx():
@@ -187,10 +199,26 @@ class EmRank:
         self.ctx._chk(rc)
         self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
 
-    def estep_bfgs_update(self, indF, alpha):
-        """E-step + F / alpha update sharing one forward pass; returns ind_lkl."""
+    def estep_bfgs_update(self, indF, alpha, posterior_ready=None):
+        """E-step + F / alpha update sharing one forward pass; returns ind_lkl.  posterior_ready() is called as
+        soon as the posteriors are complete (after the first round), see nfh_host_estep_bfgs_update_hook."""
         n = self.ctx.n_ind_owned
         lk = np.empty(n)
+        if posterior_ready is not None:
+            if self._hook is None:
+                fn = self.H.nfh_host_estep_bfgs_update_hook
+                fn.restype = C.c_int
+                fn.argtypes = [C.c_void_p, C.c_uint64, _dp, _dp, C.c_int, C.c_int, _dp, C.POINTER(C.c_uint64),
+                               _HOOK, C.c_void_p]
+                self._hook = _HOOK(lambda _user: self._hook_target())
+            self._hook_target = posterior_ready
+            rc = self.H.nfh_host_estep_bfgs_update_hook(
+                self.ctx.h, n, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp), int(self.indF_fixed),
+                int(self.alpha_fixed), lk.ctypes.data_as(_dp), self.stats.ctypes.data_as(C.POINTER(C.c_uint64)),
+                self._hook, None)
+            self.ctx._chk(rc)
+            self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
+            return lk
         rc = self.H.nfh_host_estep_bfgs_update(self.ctx.h, n, indF.ctypes.data_as(_dp), alpha.ctypes.data_as(_dp),
                                                int(self.indF_fixed), int(self.alpha_fixed), lk.ctypes.data_as(_dp),
                                                self.stats.ctypes.data_as(C.POINTER(C.c_uint64)))
@@ -215,24 +243,63 @@ class EmRank:
             ctx._chk(rc)
             self.total_rounds += int(self.stats[0]); self.total_evals += int(self.stats[1])
             return lk, fr
+        marks = [self._mark()] if self.trace is not None else None
         ctx.set_ind_params(indF, alpha)
-        if self.direct or not self.freq_est:
+        if self.mixed:
+            # posteriors leave by all-to-all as soon as they are complete, behind the remaining BFGS rounds
+            lk = self.estep_bfgs_update(indF, alpha, posterior_ready=self.exchange_posteriors_begin)
+        elif self.direct or not self.freq_est:
             lk = self.estep_bfgs_update(indF, alpha)     # posterior tiles go to their owners from the kernel
         else:
             lk = ctx.estep()
             self.exchange_posteriors_begin()             # overlaps the host/device BFGS rounds below
             self.bfgs_update(indF, alpha)
+        if marks is not None:
+            marks.append(self._mark())                   # E-step + BFGS rounds of this rank done
         fr = None
         if self.freq_est:
-            if self.direct:
+            if self.mixed:
+                self.exchange_posteriors_end()
+                self._rank_fence()                       # nobody still reads the emissions the kernel overwrites
+            elif self.direct:
                 self._rank_fence()                       # every rank's E-step stores have landed
-                fr = ctx.freq_update(1, want_freq=want_freq, out=self._freq_host)
-                self._allreduce_loge0()                  # + fence: every rank's emission stores have landed
             else:
                 self.exchange_posteriors_end()
-                fr = ctx.freq_update(1, want_freq=want_freq, out=self._freq_host)
+            if marks is not None:
+                marks.append(self._mark())               # ... and everybody else's
+            fr = ctx.freq_update(1, want_freq=want_freq, out=self._freq_host)
+            if marks is not None:
+                marks.append(self._mark())               # frequency kernel
+            if self.direct or self.mixed:
+                self._allreduce_loge0()                  # + fence: every rank's emission stores have landed
+            else:
                 self.exchange_emissions()
+            if marks is not None:
+                marks.append(self._mark())               # emissions back with their individuals
+                self.trace.append(marks)
         return lk, fr
+
+    def _mark(self):
+        import torch
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream)
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(self._ext_stream)
+        return e
+
+    def trace_summary(self):
+        """Mean milliseconds on the context stream between the marks of iteration(): E-step + BFGS of this rank,
+        wait for the other ranks (fence / posterior exchange), frequency kernel, emission exchange / fence."""
+        import torch
+        torch.cuda.synchronize()
+        if not self.trace:
+            return None
+        names = ["estep_bfgs", "wait_ranks", "freq", "exchange_back"]
+        out = {n: 0.0 for n in names}
+        for m in self.trace:
+            for k, n in enumerate(names):
+                out[n] += m[k].elapsed_time(m[k + 1]) / len(self.trace)
+        return out
 
 
 def run_em(runner: EmRank, indF, alpha, *, min_iters=10, max_iters=100, min_epsilon=1e-5, on_iteration=None):

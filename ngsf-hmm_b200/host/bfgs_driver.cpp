@@ -81,8 +81,16 @@ double minimize_with_numeric_gradient(int n, double *x, objective_fn fun, const 
 }
 
 int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, bool F_fixed, bool alpha_fixed,
-                         BfgsStats *stats, double *estep_lkl_out) {
-  if (F_fixed && alpha_fixed) return estep_lkl_out ? nfh_estep(ctx, estep_lkl_out) : NFH_OK;
+                         BfgsStats *stats, double *estep_lkl_out, stage_hook posterior_ready, void *hook_user) {
+  // The hook fires exactly once on every successful path - also for a rank that owns no individual: a multi-rank
+  // caller starts a collective in it, and a rank that skipped it would leave the others waiting.
+  bool hook_due = estep_lkl_out != nullptr && posterior_ready != nullptr;
+  auto fire_hook = [&]() { if (hook_due) { hook_due = false; posterior_ready(hook_user); } };
+  if (F_fixed && alpha_fixed) {
+    const int rc = estep_lkl_out ? nfh_estep(ctx, estep_lkl_out) : NFH_OK;
+    if (rc == NFH_OK) fire_hook();
+    return rc;
+  }
   const double inf_inv = 1.0 / 1e15;                 // 1/INF, EM.cpp:425
   struct Slot {
     std::unique_ptr<BoxLbfgs> opt;
@@ -122,6 +130,7 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
       int rc = nfh_estep(ctx, estep_lkl_out);
       if (rc != NFH_OK) return rc;
       estep_pending = false;
+      fire_hook();
     }
   }
   for (;;) {
@@ -144,6 +153,7 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
       rc = nfh_estep_with_batch(ctx, req_ind.size(), req_ind.data(), req_F.data(), req_a.data(), req_out.data(),
                                 estep_lkl_out);
       estep_pending = false;
+      if (rc == NFH_OK) fire_hook();             // the call returned: the posteriors are in
     } else {
       rc = nfh_lkl_batch(ctx, req_ind.size(), req_ind.data(), req_F.data(), req_a.data(), req_out.data());
     }
@@ -165,6 +175,7 @@ int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alp
     indF[i] = slots[i].opt->x()[0];
     alpha[i] = slots[i].opt->x()[1];
   }
+  fire_hook();                                   // no individual here (or none needed an evaluation)
   if (stats) *stats = local;
   return NFH_OK;
 }

@@ -56,7 +56,12 @@ double minimize_with_numeric_gradient(int n, double *x, objective_fn fun, const 
 // With estep_lkl_out != nullptr the E-step of the same iteration (EM.cpp:151-185) is run here as well: the
 // first batched round goes through nfh_estep_with_batch (its centre points are the E-step's parameters),
 // or, when nothing is optimised, through nfh_estep; estep_lkl_out[n_ind] receives ind_lkl.
+// posterior_ready (optional) is called once, as soon as the E-step's posteriors are complete in their window - after
+// the first round, while the remaining rounds only read the emission window - so that a multi-rank caller can start
+// moving them to the frequency side behind the rest of the optimisation.
+typedef void (*stage_hook)(void *user);
 int bfgs_update_lockstep(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, bool F_fixed, bool alpha_fixed,
-                         BfgsStats *stats, double *estep_lkl_out = nullptr);
+                         BfgsStats *stats, double *estep_lkl_out = nullptr, stage_hook posterior_ready = nullptr,
+                         void *hook_user = nullptr);
 
 }  // namespace nfh_host

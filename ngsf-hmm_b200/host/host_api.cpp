@@ -40,6 +40,20 @@ int nfh_host_estep_bfgs_update(nfh_ctx *ctx, uint64_t n_ind, double *indF, doubl
   return rc;
 }
 
+int nfh_host_estep_bfgs_update_hook(nfh_ctx *ctx, uint64_t n_ind, double *indF, double *alpha, int F_fixed,
+                                    int alpha_fixed, double *ind_lkl_out, uint64_t stats_out[3],
+                                    nfh_stage_hook posterior_ready, void *user) {
+  std::vector<double> lkl_tmp;
+  if (!ind_lkl_out) { lkl_tmp.resize(n_ind); ind_lkl_out = lkl_tmp.data(); }
+  BfgsStats st;
+  int rc = bfgs_update_lockstep(ctx, n_ind, indF, alpha, F_fixed != 0, alpha_fixed != 0, &st, ind_lkl_out,
+                                posterior_ready, user);
+  if (stats_out) {
+    stats_out[0] = st.rounds; stats_out[1] = st.evaluations; stats_out[2] = st.max_rounds_one_individual;
+  }
+  return rc;
+}
+
 int nfh_host_em_iteration(nfh_ctx *ctx, double *indF, double *alpha, int F_fixed, int alpha_fixed, int freq_est,
                           double *ind_lkl_out, double *freq_out, uint64_t stats_out[3]) {
   const uint64_t n = nfh_n_ind_owned(ctx);

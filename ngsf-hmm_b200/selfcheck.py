@@ -22,7 +22,7 @@ def _run(gl, dist_mb, device, n_ranks, rank, direct, group=None):
     ctx.set_ind_params(F, a)
     runner = EmRank(ctx, freq_est=1, group=group)
     if direct:
-        runner.enable_peer_direct()
+        runner.enable_peer_direct(posteriors=direct != "mixed")
     runner.refresh_emissions()
     lks = []
     fr = None
@@ -42,8 +42,10 @@ def _run(gl, dist_mb, device, n_ranks, rank, direct, group=None):
     return out
 
 
-def multi_rank_check(local_device: int, direct: bool = True, group=None) -> dict | None:
-    """Collective over the current process group.  Returns the comparison on rank 0 (None elsewhere):
+def multi_rank_check(local_device: int, direct=True, group=None) -> dict | None:
+    """Collective over the current process group; direct = True (kernels store posteriors and emission ratios into
+    peer windows), "mixed" (emission ratios by peer stores, posteriors by all-to-all) or False (all-to-alls).
+    Returns the comparison on rank 0 (None elsewhere):
     max deviations from the single-rank run and ``ok`` = far inside the parity tolerances
     (lkl 1e-9 relative, F / alpha / freq 1e-6, posterior 1e-8, identical Viterbi paths)."""
     import torch.distributed as dist
@@ -64,7 +66,7 @@ def multi_rank_check(local_device: int, direct: bool = True, group=None) -> dict
     dpost = np.abs(post - one["post"])
     res = {
         "case": f"{N} individuals x {S} sites, {ITERS} EM iterations + Viterbi, {world} ranks vs 1 rank",
-        "exchange": "fused peer stores" if direct else "NCCL all-to-all",
+        "exchange": {True: "fused peer stores", False: "NCCL all-to-all"}.get(direct, "mixed: posteriors by all-to-all, emission ratios by peer stores"),
         "max_abs_dF": float(np.abs(F - one["F"]).max()), "max_abs_dalpha": float(np.abs(a - one["a"]).max()),
         "max_abs_dfreq": float(np.abs(freq - one["freq"]).max()),
         "max_rel_dlkl": float((np.abs(lk - one["lk"]) / np.abs(one["lk"])).max()),

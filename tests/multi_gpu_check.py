@@ -19,7 +19,7 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     ok = True
-    for direct in (False, True):
+    for direct in (False, True, "mixed"):
         res = selfcheck.multi_rank_check(lr, direct=direct)
         if dist.get_rank() == 0:
             print(res, flush=True)

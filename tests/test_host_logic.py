@@ -58,3 +58,23 @@ def test_input_file_writers_roundtrip(tmp_path):
 
 def test_blocked_layout_shape():
     assert nfh.em.blocked_owner_layout(4, 13, 4224) == (4, 13, 4224)
+
+
+def test_posterior_ready_hook_fires_once_for_a_rank_without_individuals():
+    """A multi-rank caller starts a collective in the hook of nfh_host_estep_bfgs_update_hook: a rank that owns no
+    individual (11 individuals on 8 ranks leave two of them empty) must still reach it, exactly once.  With no
+    individual nothing touches the device context, so this runs without a GPU."""
+    import ctypes as C
+    from _host import HOST_SO
+    L = C.CDLL(HOST_SO)
+    HOOK = C.CFUNCTYPE(None, C.c_void_p)
+    calls = []
+    hook = HOOK(lambda user: calls.append(user))
+    dp = C.POINTER(C.c_double)
+    fn = L.nfh_host_estep_bfgs_update_hook
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_uint64, dp, dp, C.c_int, C.c_int, dp, C.POINTER(C.c_uint64), HOOK, C.c_void_p]
+    empty = (C.c_double * 1)()
+    stats = (C.c_uint64 * 3)()
+    rc = fn(None, 0, empty, empty, 0, 0, empty, stats, hook, None)
+    assert rc == 0 and len(calls) == 1 and stats[0] == 0
