@@ -38,7 +38,6 @@ struct nfh_ctx {
   cudaStream_t stream = nullptr;
 
   // recursion side (this rank's individuals, all sites, site-blocked layout)
-  double *dist_t = nullptr;                            // chunk-transposed copy of dist (EstepArgs::dist_t)
   double *tile_dmax = nullptr, *tile_dsum = nullptr;   // per tile of the distance vector, see nfh_upload_pos_dist
   double *dist = nullptr, *emis_recv = nullptr, *post_send = nullptr, *e0_recv = nullptr;
   double *indF = nullptr, *alpha = nullptr, *ind_lkl = nullptr;
@@ -237,7 +236,6 @@ int nfh_ctx_create(nfh_ctx **out, int device, uint64_t n_ind_total, uint64_t n_s
   const size_t plane_rec = (size_t) ctx->n_ranks * ctx->n_loc * ctx->site_block * sizeof(double);
   const size_t plane_frq = (size_t) ctx->n_ind_pad * ctx->site_block * sizeof(double);   // same number
   NFH_TRY(alloc((void **) &ctx->dist, ctx->n_sites_pad * sizeof(double), true));
-  NFH_TRY(alloc((void **) &ctx->dist_t, (size_t) ctx->n_tiles * kTile * sizeof(double), true));
   NFH_TRY(alloc((void **) &ctx->tile_dmax, ctx->n_tiles * sizeof(double), true));
   NFH_TRY(alloc((void **) &ctx->tile_dsum, ctx->n_tiles * sizeof(double), true));
   // emission-ratio windows start as 1.0 everywhere and the kernels only ever write real sites, so the
@@ -297,7 +295,7 @@ void nfh_ctx_destroy(nfh_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  void *dev[] = {ctx->dist_t, ctx->tile_dmax, ctx->tile_dsum, ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
+  void *dev[] = {ctx->tile_dmax, ctx->tile_dsum, ctx->dist, ctx->emis_recv, ctx->post_send, ctx->e0_recv, ctx->indF, ctx->alpha, ctx->ind_lkl,
                  ctx->chunk_prod, ctx->tile_prod, ctx->lkl_tile_prod, ctx->fwd_carry, ctx->bwd_carry, ctx->groups, ctx->neg_lkl,
                  ctx->vit_work, ctx->vit_maps, ctx->vit_tile_prod, ctx->vit_final, ctx->gl[0], ctx->gl[1], ctx->gl[2], ctx->freq, ctx->loge0_part, ctx->loge0_sum,
                  ctx->status, ctx->freq_passes, ctx->freq_acc, ctx->d_stage, ctx->fused.d_ticket, ctx->fused.d_row_done,
@@ -379,7 +377,7 @@ int nfh_upload_pos_dist(nfh_ctx *ctx, const double *dist_mb) {
   NFH_CUDA(cudaMemcpyAsync(ctx->dist, dist_mb, ctx->n_sites * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   // per tile: the largest distance (NaN poisons it, +inf stays +inf) and the sum, which pick the kappa
   // tier of every (individual, tile) and give the tile's scalar transition factor without a per-site sum
-  std::vector<double> tmax(ctx->n_tiles), tsum(ctx->n_tiles), dt((size_t) ctx->n_tiles * kTile, 0.0);
+  std::vector<double> tmax(ctx->n_tiles), tsum(ctx->n_tiles);
   for (uint32_t t = 0; t < ctx->n_tiles; t++) {
     const uint64_t lo = (uint64_t) t * kTile, hi = std::min(ctx->n_sites, lo + kTile);
     double mx = 0.0, sum = 0.0;
@@ -389,13 +387,10 @@ int nfh_upload_pos_dist(nfh_ctx *ctx, const double *dist_mb) {
       nan |= d != d;
       mx = d > mx ? d : mx;
       sum += d;
-      const uint64_t k = s - lo;                       // site k = 33 thread + j of the tile
-      dt[lo + (k % kChunk) * kScanThreads + k / kChunk] = d;
     }
     tmax[t] = nan ? std::nan("") : mx;
     tsum[t] = sum;
   }
-  NFH_CUDA(cudaMemcpyAsync(ctx->dist_t, dt.data(), dt.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   NFH_CUDA(cudaMemcpyAsync(ctx->tile_dmax, tmax.data(), ctx->n_tiles * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   NFH_CUDA(cudaMemcpyAsync(ctx->tile_dsum, tsum.data(), ctx->n_tiles * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   NFH_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -489,7 +484,7 @@ int nfh_freq_update(nfh_ctx *ctx, int method, int posterior_is_zero, double *fre
 static EstepArgs estep_args(nfh_ctx *ctx) {
   EstepArgs a;
   a.emis = ctx->emis_recv; a.dist = ctx->dist; a.indF = ctx->indF; a.alpha = ctx->alpha;
-  a.dist_t = ctx->dist_t; a.tile_dmax = ctx->tile_dmax; a.tile_dsum = ctx->tile_dsum;
+  a.tile_dmax = ctx->tile_dmax; a.tile_dsum = ctx->tile_dsum;
   a.loge0_sum = ctx->loge0_sum + ctx->ind_begin;
   a.chunk_prod = ctx->chunk_prod; a.tile_prod = ctx->tile_prod; a.fwd_carry = ctx->fwd_carry; a.bwd_carry = ctx->bwd_carry;
   a.post = ctx->post_send; a.ind_lkl = ctx->ind_lkl; a.status = ctx->status;

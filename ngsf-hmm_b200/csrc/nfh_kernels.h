@@ -49,7 +49,6 @@ struct EstepFusedState {
 struct EstepArgs {
   const double *emis;        // emission ratio, blocked [n_ranks][n_rows][site_block]
   const double *dist;        // [n_ranks * site_block] Mb
-  const double *dist_t;      // the same distances, chunk-transposed per tile: site 33 t + j of tile T at T*4224 + j*128 + t
   const double *tile_dmax, *tile_dsum;   // per tile: largest distance and sum of distances (kappa tiers, nfh_device.cuh)
   const double *indF, *alpha;
   const double *loge0_sum;   // [n_rows] sum over sites of log e0
