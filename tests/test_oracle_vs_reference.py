@@ -70,3 +70,28 @@ def test_iteration_bit_identical(ref, oracle, case):
     for i in range(N):
         _, p = oracle.viterbi(after["e_prob"][i], d.dist_mb, after["indF"][i], after["alpha"][i])
         assert (p == path[i]).all()
+
+
+def test_fixed_parameter_iteration_changes_nothing_but_the_posterior(ref, oracle):
+    """configs[4] semantics (--indF_fixed --alpha_fixed --freq_est 0): the reference's iter_EM then leaves freq, F,
+    alpha and every emission untouched (EM.cpp:188-271 is skipped) and only produces ind_lkl and the posterior - which
+    is why a multi-GPU run of that configuration has nothing to exchange per iteration (nfh_peer_direct mode 2).  The
+    oracle's E-step must reproduce both bit for bit."""
+    d = sim.simulate(5, 900, seed=404, freq=(0.05, 0.5), indF=(0.05, 0.5), alpha=0.03)
+    freq0 = np.clip(d.true_freq, 0.01, 0.49)
+    F0 = np.clip(d.true_F, 1e-3, 1 - 1e-3); a0 = d.true_alpha.copy()
+    st = ref.state(d.log_gl, d.dist_mb, freq0, F0, a0, freq_est=0, indF_fixed=True, alpha_fixed=True)
+    before = st.get()
+    st.iter_EM()
+    after = st.get()
+    st.iter_EM()
+    again = st.get()
+    st.close()
+    for key in ("freq", "indF", "alpha", "e_prob"):
+        np.testing.assert_array_equal(after[key], before[key])
+    for key in ("ind_lkl", "marg1"):                      # a second iteration repeats the first
+        np.testing.assert_array_equal(again[key], after[key])
+    status, marg1, lk = oracle.estep(before["e_prob"], d.dist_mb, F0, a0)
+    assert status == 0
+    np.testing.assert_array_equal(lk, after["ind_lkl"])
+    np.testing.assert_array_equal(marg1, after["marg1"])
