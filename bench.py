@@ -62,7 +62,11 @@ def parse_args():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_parity_check", action="store_true")
     ap.add_argument("--trace", action="store_true", help="multi-rank: per-phase stream times of every rank (extra untimed leg)")
-    ap.add_argument("--cpu_sites", type=int, default=20000, help="sites of the bounded CPU sample (reference arm)")
+    ap.add_argument("--cpu_sites", type=int, default=None,
+                    help="sites of the bounded CPU sample (reference arm); default: sized from a calibration "
+                         "iteration so that the W + K iterations fit --cpu_budget_s, at most 20,000")
+    ap.add_argument("--cpu_budget_s", type=float, default=float(os.environ.get("NFH_REF_BUDGET_S", "150")),
+                    help="wall-clock target of the whole reference arm (W + K iterations)")
     a = ap.parse_args()
     cfg = CONFIGS[a.config]
     a.n_ind = a.n_ind or cfg["n_ind"]
@@ -197,18 +201,37 @@ def reference_arm(args, as_cpu_baseline=False):
     from ngsf_hmm_b200 import sim
     cores = os.cpu_count() or 1
     N = min(args.n_ind, 100)                    # the reference holds ~250 B per individual-site
-    S = args.cpu_sites
-    d = sim.simulate_torch(N, S, device="cpu", seed=1002, site_chunk=1 << 14)
     threads = min(cores, N)
-    ref = Ref()
-    if args.fixed:
-        st = ref.state(d["log_gl"].numpy(), d["dist_mb"], np.clip(d["true_freq"], 0.01, 0.49),
-                       np.clip(d["true_F"], 1e-6, 1 - 1e-6), d["true_alpha"], freq_est=0, n_threads=threads,
-                       indF_fixed=True, alpha_fixed=True)
-    else:
-        st = ref.state(d["log_gl"].numpy(), d["dist_mb"], START_FREQ, START_F, START_ALPHA, freq_est=1,
-                       n_threads=threads)
     steps, warm = (1, 0) if as_cpu_baseline else (args.steps, args.warmup)
+    ref = Ref()
+
+    def make_state(S):
+        d = sim.simulate_torch(N, S, device="cpu", seed=1002, site_chunk=1 << 14)
+        if args.fixed:
+            return ref.state(d["log_gl"].numpy(), d["dist_mb"], np.clip(d["true_freq"], 0.01, 0.49),
+                             np.clip(d["true_F"], 1e-6, 1 - 1e-6), d["true_alpha"], freq_est=0, n_threads=threads,
+                             indF_fixed=True, alpha_fixed=True)
+        return ref.state(d["log_gl"].numpy(), d["dist_mb"], START_FREQ, START_F, START_ALPHA, freq_est=1,
+                         n_threads=threads)
+
+    # The sample is bounded by TIME: the driver chooses K and W, and a reference iteration costs ~1e-5 s per
+    # individual-site, so a fixed site count would run for many minutes at large K.  One calibration iteration on
+    # 2,000 sites (the first EM iteration, the one with the most BFGS rounds) gives the rate; the sample then gets
+    # as many sites as W + K iterations can cover within --cpu_budget_s, between 2,000 and 20,000.
+    sized = "--cpu_sites"
+    S = args.cpu_sites
+    if S is None:
+        S_cal = 2000
+        st = make_state(S_cal)
+        t0 = time.perf_counter()
+        st.iter_EM()
+        t_cal = time.perf_counter() - t0
+        st.close()
+        S = int(0.8 * args.cpu_budget_s / max(steps + warm, 1) / max(t_cal, 1e-6) * S_cal)
+        S = max(2000, min(20000, S // 500 * 500))
+        sized = (f"a calibration iteration on {S_cal} sites ({t_cal:.2f} s) and a budget of {args.cpu_budget_s:.0f} s "
+                 f"for {warm} + {steps} iterations")
+    st = make_state(S)
     for _ in range(warm):
         st.iter_EM()
     t0 = time.perf_counter()
@@ -220,16 +243,19 @@ def reference_arm(args, as_cpu_baseline=False):
     cb = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
           "sample": f"{N} individuals x {S} sites of the same synthetic workload, {warm} warm-up + {steps} timed "
                     f"iter_EM() call(s) of the unmodified reference in-process (oracle/_ref), --n_threads {threads} "
-                    f"of {cores} host cores; its frequency loop is serial.  A per-unit RATE on a sample, not the same "
-                    f"job timed twice"}
+                    f"of {cores} host cores; its frequency loop is serial; sites chosen by {sized}.  A per-unit RATE "
+                    f"on a sample, not the same job timed twice"}
     if as_cpu_baseline:
         return cb
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.cfg_name} sample: {N} ind x {S} sites, " +
-                                   ("fixed parameters, --freq_est 0" if args.fixed else
-                                    "--freq_est 1, --freq 0.1 --indF 0.1,0.2")},
+            "config": {"workload": workload_text(args, args.n_ind * max(args.gpus, 1)),
+                       "step": ("one fixed-parameter EM iteration = forward-backward E-step with posteriors"
+                                if args.fixed else
+                                "one EM iteration = E-step + BFGS(F,alpha) per individual + freq EM + emission refresh"),
+                       "sample": f"each step runs on a bounded sample of that workload: {N} individuals x {S} sites "
+                                 f"(rank 0's host cores only; see cpu_baseline.sample)"},
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 

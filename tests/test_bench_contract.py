@@ -23,3 +23,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+@pytest.mark.ref
+def test_reference_arm_sizes_its_sample_from_a_time_budget():
+    """Without --cpu_sites the sample is sized from one calibration iteration so that W + K iterations fit the
+    budget (the driver chooses K and W); the floor is 2,000 sites."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup",
+                        "0", "--cpu_budget_s", "0.5"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    assert "100 individuals x 2000 sites" in d["cpu_baseline"]["sample"]
+    assert "calibration iteration" in d["cpu_baseline"]["sample"]
+    assert d["config"]["workload"].startswith("configs[1] per GPU: 100 individuals x 1000000 sites")
