@@ -123,6 +123,7 @@ BoxLbfgs::BoxLbfgs(int n, int m, const double *x0, const double *lower, const do
   ss_.assign((size_t) m * m, 0.0);
   wt_.assign((size_t) m * m, 0.0);
   wn_.assign((size_t) 4 * m * m, 0.0);
+  wn1_.assign((size_t) 4 * m * m, 0.0);
   z_.assign(n, 0.0); r_.assign(n, 0.0); d_.assign(n, 0.0); t_.assign(n, 0.0); brk_.assign(n, 0.0);
   p_.assign(2 * m, 0.0); c_.assign(2 * m, 0.0); wbp_.assign(2 * m, 0.0); v_.assign(2 * m, 0.0);
   wv_.assign(2 * m, 0.0);
@@ -394,36 +395,100 @@ void BoxLbfgs::pick_free_variables() {
 // Build and factorise the 2col x 2col matrix
 //   K = [ D + Y'ZZ'Y/theta     -L_a' + R_z'  ]
 //       [ -L_a + R_z           theta S'AA'S  ]
-// (Z: free variables, A: active ones) as L E L'.  The reference code keeps
-// the inner products incrementally; with the few variables of this problem
-// they are simply recomputed from the stored pairs.
+// (Z: free variables, A: active ones) as L E L'.
+//
+// The inner products behind K live in wn1_ and are maintained INCREMENTALLY, as the published code does
+// (formk): a new pair adds its row / column computed over the current free and active sets, the older entries
+// are corrected by the variables that entered or left the free set since the previous iteration, and nothing
+// else ever touches them.  This is deliberately not a recomputation from the stored pairs: an iteration
+// that skips the subspace step (no free variable at the Cauchy point, or an empty memory) also skips this
+// bookkeeping in the reference (bfgs.cpp:986-1008), so a pair stored in such an iteration never gets its row
+// and a change of the free set in such an iteration is never applied - from then on the reference minimises
+// over a K that differs from the true one, and takes different steps.  Iterate-for-iterate parity needs the
+// same history dependence (found by tests/test_lbfgsb.py::test_random_objectives_same_iterates: 10 of 200
+// random boxed problems diverged with the recomputed K).  wn1_ also survives forget_memory(), as there.
+//   wn1_ (2m x 2m, lower triangle used):  [ Y'ZZ'Y            ]      rows/cols 0..m-1   : y index
+//                                         [ L_a + R_z  S'AA'S ]      rows/cols m..2m-1 : s index
 bool BoxLbfgs::form_reduced_system() {
   const int n = n_, m = m_, col = col_, ld = 2 * m_;
-  auto col_of = [&](int j) { return (head_ + j) % m; };
-  for (int iy = 0; iy < col; iy++) {
-    const int is = col + iy;
-    const int pi = col_of(iy);
-    for (int jy = 0; jy <= iy; jy++) {
-      const int js = col + jy;
-      const int pj = col_of(jy);
-      double yy = 0.0, ss = 0.0;
-      for (int k = 0; k < nfree_; k++) { const int v = index_[k]; yy += wy_[v + pi * n] * wy_[v + pj * n]; }
-      for (int k = nfree_; k < n; k++) { const int v = index_[k]; ss += ws_[v + pi * n] * ws_[v + pj * n]; }
-      wn_[jy + iy * ld] = yy / theta_;
-      wn_[js + is * ld] = ss * theta_;
-    }
-    // block (1,2): entry (jy, is) = -L_a'(jy,iy) for jy < iy, R_z'(...) for jy >= iy
-    for (int jy = 0; jy < col; jy++) {
-      const int pj = col_of(jy);
-      double acc = 0.0;
-      if (jy < iy) {
-        for (int k = nfree_; k < n; k++) { const int v = index_[k]; acc += ws_[v + pi * n] * wy_[v + pj * n]; }
-        wn_[jy + is * ld] = -acc;
-      } else {
-        for (int k = 0; k < nfree_; k++) { const int v = index_[k]; acc += ws_[v + pi * n] * wy_[v + pj * n]; }
-        wn_[jy + is * ld] = acc;
+  auto slot = [&](int j) { return (head_ + j) % m; };            // storage column of the j-th oldest pair
+  auto yy = [&](int i, int j) -> double & { return wn1_[i + j * ld]; };
+  auto ss = [&](int i, int j) -> double & { return wn1_[(m + i) + (m + j) * ld]; };
+  auto sy = [&](int i, int j) -> double & { return wn1_[(m + i) + j * ld]; };     // s index i, y index j
+  int n_old = col;                          // leading pairs that only see the change of the free set
+  if (updatd_) {
+    if (iupdat_ > m) {                      // the oldest pair was dropped: everything moves up and left by one
+      for (int j = 0; j < m - 1; j++) {
+        for (int i = j; i < m - 1; i++) {
+          yy(i, j) = yy(i + 1, j + 1);
+          ss(i, j) = ss(i + 1, j + 1);
+        }
+        for (int i = 0; i < m - 1; i++) sy(i, j) = sy(i + 1, j + 1);
       }
     }
+    const int last = col - 1, pl = slot(last);
+    for (int j = 0; j < col; j++) {         // row of the newest pair
+      const int pj = slot(j);
+      double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+      for (int k = 0; k < nfree_; k++) { const int v = index_[k]; t1 += wy_[v + pl * n] * wy_[v + pj * n]; }
+      for (int k = nfree_; k < n; k++) {
+        const int v = index_[k];
+        t2 += ws_[v + pl * n] * ws_[v + pj * n];
+        t3 += ws_[v + pl * n] * wy_[v + pj * n];
+      }
+      yy(last, j) = t1;
+      ss(last, j) = t2;
+      sy(last, j) = t3;                     // L_a part (active variables); the diagonal is overwritten below
+    }
+    for (int i = 0; i < col; i++) {         // column of the newest pair: R_z part (free variables)
+      const int pi = slot(i);
+      double t3 = 0.0;
+      for (int k = 0; k < nfree_; k++) { const int v = index_[k]; t3 += ws_[v + pi * n] * wy_[v + pl * n]; }
+      sy(i, last) = t3;
+    }
+    n_old = col - 1;
+  }
+  // older entries: add the entering variables to the free-set sums and take the leaving ones out (and the
+  // other way round for the active-set sums), in the order the sets were collected
+  for (int i = 0; i < n_old; i++) {
+    const int pi = slot(i);
+    for (int j = 0; j <= i; j++) {
+      const int pj = slot(j);
+      double e_yy = 0.0, e_ss = 0.0, l_yy = 0.0, l_ss = 0.0;
+      for (int k = 0; k < nenter_; k++) {
+        const int v = indx2_[k];
+        e_yy += wy_[v + pi * n] * wy_[v + pj * n];
+        e_ss += ws_[v + pi * n] * ws_[v + pj * n];
+      }
+      for (int k = ileave_; k < n; k++) {
+        const int v = indx2_[k];
+        l_yy += wy_[v + pi * n] * wy_[v + pj * n];
+        l_ss += ws_[v + pi * n] * ws_[v + pj * n];
+      }
+      yy(i, j) = yy(i, j) + e_yy - l_yy;
+      ss(i, j) = ss(i, j) - e_ss + l_ss;
+    }
+  }
+  for (int i = 0; i < n_old; i++) {
+    const int pi = slot(i);
+    for (int j = 0; j < n_old; j++) {
+      const int pj = slot(j);
+      double e = 0.0, l = 0.0;
+      for (int k = 0; k < nenter_; k++) { const int v = indx2_[k]; e += ws_[v + pi * n] * wy_[v + pj * n]; }
+      for (int k = ileave_; k < n; k++) { const int v = indx2_[k]; l += ws_[v + pi * n] * wy_[v + pj * n]; }
+      if (i <= j) sy(i, j) = sy(i, j) + e - l;      // R_z: over the free variables
+      else sy(i, j) = sy(i, j) - e + l;             // L_a: over the active variables
+    }
+  }
+  // upper triangle of K from the inner products
+  for (int iy = 0; iy < col; iy++) {
+    const int is = col + iy;
+    for (int jy = 0; jy <= iy; jy++) {
+      wn_[jy + iy * ld] = yy(iy, jy) / theta_;
+      wn_[(col + jy) + is * ld] = ss(iy, jy) * theta_;
+    }
+    for (int jy = 0; jy < iy; jy++) wn_[jy + is * ld] = -sy(iy, jy);
+    for (int jy = iy; jy < col; jy++) wn_[jy + is * ld] = sy(iy, jy);
     wn_[iy + iy * ld] += sy_[iy + iy * m];
   }
   // Cholesky of the (1,1) block, L^-1 applied to the (1,2) block

@@ -77,6 +77,8 @@ class BoxLbfgs {
 
   // limited-memory matrices (column j of ws/wy = j-th stored correction, circular from head_)
   std::vector<double> ws_, wy_, sy_, ss_, wt_, wn_;
+  // inner products behind the reduced system, kept incrementally across iterations (see form_reduced_system)
+  std::vector<double> wn1_;
   // work vectors
   std::vector<double> z_, r_, d_, t_, xcp_c_, p_, c_, wbp_, v_, wv_;
   std::vector<int> index_, iwhere_, indx2_, iorder_;
