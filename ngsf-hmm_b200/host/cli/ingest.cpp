@@ -71,9 +71,11 @@ inline void call_genotype(double *g) {
   }
 }
 
+// chomp (gen_func.cpp:192-199) removes ONE trailing character, '\n' or '\r': a CRLF line keeps its '\r', which
+// then hides the last numeric field of a GENO line from split() - reproduced, not repaired
 void chomp(char *s) {
-  size_t n = strlen(s);
-  while (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) s[--n] = '\0';
+  const size_t n = strlen(s);
+  if (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) s[n - 1] = '\0';
 }
 
 // numeric fields of a whitespace-separated line; tokens that are not entirely a number are dropped
@@ -102,23 +104,46 @@ void read_positions(RunState &st) {
   const char *fn = "read_dist";
   gzFile fh = gzopen(o.pos.c_str(), "r");
   if (!fh) fatal("read_file", "cannot open file!");
+  // read_file (gen_func.cpp:236-275): every line that is neither empty nor a '#' comment; the end-of-file test
+  // comes AFTER the read, so a last line without a newline is lost (and the line count below then fails)
   std::vector<char> buf(kLineMax);
+  std::string lines;                       // kept lines, each NUL-terminated
+  std::vector<size_t> start;
+  for (;;) {
+    buf[0] = '\0';
+    gzgets(fh, buf.data(), (int) kLineMax);
+    if (gzeof(fh)) break;
+    chomp(buf.data());
+    if (buf[0] == '\0' || buf[0] == '#') continue;
+    start.push_back(lines.size());
+    lines.append(buf.data(), strlen(buf.data()) + 1);
+  }
+  gzclose(fh);
+  // read_split (read_data.cpp:129-153): tab-separated, the same number of fields on every line
+  if (start.empty()) fatal("read_split", "cannot open file!");
+  size_t n_fields = 0;
+  for (size_t r = 0; r < start.size(); r++) {
+    size_t n = 1;
+    for (const char *p = lines.data() + start[r]; *p; p++) n += *p == '\t';
+    if (n_fields == 0) n_fields = n;
+    if (n != n_fields) fatal("read_split", "invalid number of fields in file!");
+  }
+  if (start.size() != o.n_sites) fatal(fn, "wrong number of lines in POS file!");
+  if (n_fields < 2) fatal(fn, "wrong POS file format!");
+
   st.dist_mb.assign(o.n_sites, INFINITY);
   std::string prev_chr;
   unsigned long prev_pos = 0;
-  uint64_t s = 0;
-  while (gzgets(fh, buf.data(), (int) kLineMax) != nullptr) {
-    chomp(buf.data());
-    if (buf[0] == '\0' || buf[0] == '#') continue;            // read_file skips these (gen_func.cpp:257-260)
-    if (s >= o.n_sites) fatal(fn, "wrong number of lines in POS file!");
-    char *tab = strchr(buf.data(), '\t');
-    if (!tab) fatal(fn, "wrong POS file format!");
+  for (uint64_t s = 0; s < o.n_sites; s++) {
+    char *chr = &lines[start[s]];
+    char *tab = strchr(chr, '\t');
     *tab = '\0';
-    const char *chr = buf.data();
     char *pos_txt = tab + 1;
     char *tab2 = strchr(pos_txt, '\t');
     if (tab2) *tab2 = '\0';
     const double pos = strtod(pos_txt, nullptr);
+    // the reference treats a zero position as a header and then never leaves its loop (read_data.cpp:188-196);
+    // the one place where this reader stops with a message of its own
     if (pos == 0) fatal(fn, "header found in POS file (prefix header lines with #)");
     if (prev_chr.empty()) prev_chr = chr;
     if (prev_chr == chr) {
@@ -129,10 +154,7 @@ void read_positions(RunState &st) {
       prev_chr = chr;
     }
     prev_pos = strtoul(pos_txt, nullptr, 0);
-    s++;
   }
-  gzclose(fh);
-  if (s != o.n_sites) fatal(fn, "wrong number of lines in POS file!");
   for (uint64_t i = 0; i < o.n_sites; i++) st.dist_mb[i] /= 1e6;   // bp -> Mb, ngsF-HMM.cpp:85-86
   if (o.verbose >= 7)
     for (uint64_t i = 0; i < o.n_sites && i < 10; i++) printf("%f\n", st.dist_mb[i]);

@@ -260,6 +260,34 @@ void *ref_state_create(uint64_t N, uint64_t S, const double *gl, const double *d
   return st;
 }
 
+/* ---- f-2: input ingest, exactly what main() does between parse_cmd_args and init_output
+ * (ngsF-HMM.cpp:47-117): binary/gz detection by file name, read_dist (read_data.cpp:165-218) scaled to Mb,
+ * read_geno (read_data.cpp:13-116), optional call_geno and the second normalisation.
+ * Outputs: gl_out site-major S x N x 3 (the layout of the binary input file), dist_out S (Mb).
+ * Errors exit(-1) as in the reference - call with valid files only (error texts are compared through the
+ * two binaries instead). */
+void ref_read_inputs(const char *geno_file, const char *pos_file, uint64_t N, uint64_t S, int in_lkl, int in_loglkl,
+                     int call_genotypes, double *gl_out, double *dist_out) {
+  char *geno = strdup(geno_file), *pos = strdup(pos_file);
+  bool lkl_flag = in_lkl != 0, loglkl_flag = in_loglkl != 0, in_bin;
+  const char *dot = strrchr(geno, '.');
+  if (dot && strcmp(dot, ".gz") == 0) in_bin = false;
+  else { in_bin = true; lkl_flag = true; }
+  quiet_stdout q(true);
+  double *pd = read_dist(pos, 0, S);
+  for (uint64_t s = 0; s < S; s++) dist_out[s] = pd[s] / 1e6;
+  free_ptr((void *) pd);
+  double ***g = read_geno(geno, in_bin, lkl_flag, &loglkl_flag, N, S);
+  for (uint64_t i = 0; i < N; i++)
+    for (uint64_t s = 1; s <= S; s++) {
+      if (call_genotypes) call_geno(g[i][s], N_GENO);
+      post_prob(g[i][s], g[i][s], NULL, N_GENO);
+      for (int k = 0; k < 3; k++) gl_out[((s - 1) * N + i) * 3 + k] = g[i][s][k];
+    }
+  free_ptr((void ***) g, N, S + 1);
+  free(geno); free(pos);
+}
+
 void ref_state_iter_EM(void *h) {
   ref_state *st = (ref_state *) h;
   quiet_stdout q(true);
