@@ -7,6 +7,7 @@
 // stream bit for bit).  "e" runs the frequency EM with F = 0 on the device.
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -164,6 +165,13 @@ void init_start_values(RunState &st, unsigned seed) {
   if (o.verbose >= 1) printf("==> Calculating initial emission probabilities\n");
   if (estimate) {
     check(st, nfh_group_freq_init(st.grp, st.freq.data()), "nfh_freq_update");   // est_maf with F = 0
+    if (o.freq_est != 1 && S > 1) {
+      // parse_args.cpp:316-318 estimates a site only `if(freq_est == 1 || s == 1)`: with --freq_est 0 the first
+      // site gets its estimate and every other site stays at the lower limit of the range (0.01) for the run
+      std::fill(st.freq.begin() + 1, st.freq.end(), flo);
+      check(st, nfh_group_set_freq(st.grp, st.freq.data()), "nfh_set_freq");
+      check(st, nfh_group_refresh_emissions(st.grp, 0), "nfh_emission_refresh");
+    }
   } else {
     check(st, nfh_group_set_freq(st.grp, st.freq.data()), "nfh_set_freq");
     check(st, nfh_group_refresh_emissions(st.grp, 0), "nfh_emission_refresh");
