@@ -59,9 +59,9 @@ int split_numbers(const char *text, const char *seps, double *out, int cap) {
   return n;
 }
 
-void chomp(char *s) {
-  size_t n = strlen(s);
-  while (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) s[--n] = '\0';
+void chomp(char *s) {   // ONE trailing '\n' or '\r', as gen_func.cpp:192-199 (a CRLF file keeps its '\r' and fails the field count)
+  const size_t n = strlen(s);
+  if (n && (s[n - 1] == '\n' || s[n - 1] == '\r')) s[n - 1] = '\0';
 }
 
 }  // namespace

@@ -288,6 +288,33 @@ void ref_read_inputs(const char *geno_file, const char *pos_file, uint64_t N, ui
   free(geno); free(pos);
 }
 
+/* ---- f-3: start values, exactly init_output (parse_args.cpp:229-419) on a params with uniform GL
+ * (the GL only matter for --freq e, which the GPU tests cover).  Strings as given on the command line. */
+void ref_init_start_values(const char *indF_arg, const char *freq_arg, unsigned seed, uint64_t N, uint64_t S,
+                           int freq_est, double *indF_out, double *alpha_out, double *freq_out) {
+  params *p = new params;
+  init_pars(p);
+  p->n_ind = N; p->n_sites = S; p->freq_est = freq_est; p->verbose = 0; p->seed = seed;
+  p->in_indF = strdup(indF_arg); p->in_freq = strdup(freq_arg);
+  p->geno_lkl = init_ptr(N, S + 1, N_GENO, log((double) 1 / 3));
+  p->geno_lkl_s = transp_matrix(p->geno_lkl, N, S + 1);
+  {
+    quiet_stdout q(true);
+    init_output(p);
+  }
+  for (uint64_t i = 0; i < N; i++) { indF_out[i] = p->indF[i]; alpha_out[i] = p->alpha[i]; }
+  for (uint64_t s = 0; s < S; s++) freq_out[s] = p->freq[s + 1];
+  free_ptr((void ***) p->geno_lkl, N, S + 1);
+  free_ptr((void **) p->geno_lkl_s, S + 1);
+  free_ptr((void *) p->freq); free_ptr((void *) p->indF); free_ptr((void *) p->alpha);
+  free_ptr((void **) p->path, N);
+  free_ptr((void ***) p->marg_prob, N, S + 1);
+  free_ptr((void ***) p->e_prob, N, S + 1);
+  free_ptr((void *) p->ind_lkl);
+  free(p->in_indF); free(p->in_freq);
+  delete p;
+}
+
 void ref_state_iter_EM(void *h) {
   ref_state *st = (ref_state *) h;
   quiet_stdout q(true);
