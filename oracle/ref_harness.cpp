@@ -315,6 +315,38 @@ void ref_init_start_values(const char *indF_arg, const char *freq_arg, unsigned 
   delete p;
 }
 
+/* ---- f-1: output files, exactly print_iter (EM.cpp:293-380) on a params filled from flat arrays.
+ * gl: site-major S x N x 3 normalised log GL (used by the .geno posterior). */
+void ref_print_iter(const char *out_prefix, uint64_t N, uint64_t S, double tot_lkl, const double *indF,
+                    const double *alpha, const double *freq, const double *ind_lkl, const char *path,
+                    const double *marg1, const double *gl) {
+  params *p = new params;
+  init_pars(p);
+  p->n_ind = N; p->n_sites = S; p->tot_lkl = tot_lkl;
+  p->indF = init_ptr(N, 0.0); p->alpha = init_ptr(N, 0.0); p->ind_lkl = init_ptr(N, 0.0);
+  for (uint64_t i = 0; i < N; i++) { p->indF[i] = indF[i]; p->alpha[i] = alpha[i]; p->ind_lkl[i] = ind_lkl[i]; }
+  p->freq = init_ptr(S + 1, 0.0);
+  p->freq[0] = -1;
+  for (uint64_t s = 0; s < S; s++) p->freq[s + 1] = freq[s];
+  p->path = init_ptr(N, S + 1, (const char *) '\0');
+  p->marg_prob = init_ptr(N, S + 1, N_STATES, 0.0);
+  p->geno_lkl = init_ptr(N, S + 1, N_GENO, 0.0);
+  for (uint64_t i = 0; i < N; i++)
+    for (uint64_t s = 0; s < S; s++) {
+      p->path[i][s + 1] = path[i * S + s];
+      p->marg_prob[i][s + 1][1] = marg1[i * S + s];
+      for (int g = 0; g < 3; g++) p->geno_lkl[i][s + 1][g] = gl[(s * N + i) * 3 + g];
+    }
+  char *prefix = strdup(out_prefix);
+  print_iter(prefix, p);
+  free(prefix);
+  free_ptr((void ***) p->geno_lkl, N, S + 1);
+  free_ptr((void ***) p->marg_prob, N, S + 1);
+  free_ptr((void **) p->path, N);
+  free_ptr((void *) p->freq); free_ptr((void *) p->indF); free_ptr((void *) p->alpha); free_ptr((void *) p->ind_lkl);
+  delete p;
+}
+
 void ref_state_iter_EM(void *h) {
   ref_state *st = (ref_state *) h;
   quiet_stdout q(true);
