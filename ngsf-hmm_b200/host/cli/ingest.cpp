@@ -160,11 +160,10 @@ void read_positions(RunState &st) {
     for (uint64_t i = 0; i < o.n_sites && i < 10; i++) printf("%f\n", st.dist_mb[i]);
 }
 
-void read_genotypes(RunState &st) {
+// main()'s look at the GENO file before anything is read (ngsF-HMM.cpp:47-66): text or binary by the file name,
+// and a binary file must hold exactly n_sites x n_ind x 3 doubles
+void inspect_geno_file(RunState &st) {
   Options &o = st.opt;
-  const char *fn = "read_geno";
-  const uint64_t N = o.n_ind, S = o.n_sites;
-
   struct stat sb;
   if (stat(o.geno.c_str(), &sb) != 0) fatal("main", "cannot check GENO file size!");
   const char *dot = strrchr(o.geno.c_str(), '.');
@@ -175,8 +174,14 @@ void read_genotypes(RunState &st) {
     if (o.verbose >= 1) printf("==> BINARY input file (always lkl)\n");
     o.in_bin = true;
     o.lkl = true;
-    if (S != (uint64_t) sb.st_size / sizeof(double) / N / 3) fatal("main", "invalid/corrupt genotype input file!");
+    if (o.n_sites != (uint64_t) sb.st_size / sizeof(double) / o.n_ind / 3) fatal("main", "invalid/corrupt genotype input file!");
   }
+}
+
+void read_genotypes(RunState &st) {
+  Options &o = st.opt;
+  const char *fn = "read_geno";
+  const uint64_t N = o.n_ind, S = o.n_sites;
   if (o.verbose >= 1) printf("> GENO data\n");
 
   st.log_gl.reset(new double[S * N * 3]);

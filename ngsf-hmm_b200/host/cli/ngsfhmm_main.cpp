@@ -15,6 +15,7 @@ int main(int argc, char **argv) {
     warn("main", "adjusting threads (--n_threads) to match number of individuals!");
     st.opt.n_threads = (unsigned) st.opt.n_ind;
   }
+  inspect_geno_file(st);
   if (st.opt.verbose >= 1) printf("==> Reading data\n> Sites coordinates\n");
   read_positions(st);
   read_genotypes(st);

@@ -53,6 +53,7 @@ void check(RunState &st, int rc, const char *where);   // maps C-ABI status to f
 // options.cpp
 void parse_options(Options &o, int argc, char **argv);
 // ingest.cpp
+void inspect_geno_file(RunState &st);   // binary / gz text by name, size check; before anything is read
 void read_positions(RunState &st);
 void read_genotypes(RunState &st);
 // startvalues.cpp

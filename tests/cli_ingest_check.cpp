@@ -12,6 +12,7 @@ using namespace nfh_cli;
 int main(int argc, char **argv) {
   RunState st;
   parse_options(st.opt, argc, argv);
+  inspect_geno_file(st);
   read_positions(st);
   read_genotypes(st);
   const std::string base = st.opt.out;
