@@ -1,13 +1,15 @@
 """CPU: the drop-in binary's whole host side against the reference binary, BYTE FOR BYTE.
 
-The PRODUCT's command-line sources (host/cli/*.cpp) and host library sources (lbfgsb, bfgs_driver, host_api),
-compiled as they are, are linked against a fake device whose arithmetic is the oracle's (tests/fake_device_oracle.c,
-tests/fake_group_oracle.c; the oracle equals the reference bit for bit) instead of the CUDA library.  In that build
+The PRODUCT's command-line sources (host/cli/*.cpp) and host library sources (lbfgsb, bfgs_driver, host_api, group),
+compiled as they are, are linked against a fake device whose arithmetic is the oracle's
+(tests/fake_device_ranks_oracle.c: the context-level C ABI with its multi-rank geometry, exchange windows and
+peer-direct stores; the oracle equals the reference bit for bit) instead of the CUDA library.  In that build
 only the device arithmetic is replaced - by the reference's own - so `.indF`, `.ibd`, `.geno` and the progress
 output must equal the unmodified reference binary's exactly, for every input mode and flag combination: readers,
 start values (numbers, files, random, estimated), iteration control and stop rule, the lockstep optimiser, Viterbi
-hand-over, output formats, --log dumps, replicates.  (That the kernels compute the oracle's functions is what the
-GPU tests show.)"""
+hand-over, output formats, --log dumps, replicates - and for --n_gpus 2 / 3 / 8, where est_maf still sums over the
+individuals in index order at the owner of a site, so the sharded run must not differ in a single bit.  (That the
+kernels compute the oracle's functions is what the GPU tests show.)"""
 import os
 import subprocess
 
@@ -30,7 +32,7 @@ def ours(tmp_path_factory):
            os.path.join(ROOT, "oracle")]
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     objs = []
-    srcs = [os.path.join(HOST, f) for f in ("lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp")]
+    srcs = [os.path.join(HOST, f) for f in ("lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp", "group.cpp")]
     srcs += [os.path.join(HOST, "cli", f) for f in ("options.cpp", "ingest.cpp", "startvalues.cpp", "em_loop.cpp",
                                                      "report.cpp", "ngsfhmm_main.cpp")]
     procs = []
@@ -38,7 +40,7 @@ def ours(tmp_path_factory):
         o = os.path.join(d, os.path.basename(src) + ".o")
         procs.append(subprocess.Popen(["g++", "-O2", "-std=c++17", "-ffp-contract=off"] + inc + ["-c", src, "-o", o]))
         objs.append(o)
-    for name in ("fake_device_oracle", "fake_group_oracle"):
+    for name in ("fake_device_ranks_oracle",):
         o = os.path.join(d, name + ".o")
         procs.append(subprocess.Popen(["gcc", "-O2", "-std=c11", "-ffp-contract=off"] + inc +
                                       ["-c", os.path.join(ROOT, "tests", name + ".c"), "-o", o]))
@@ -88,8 +90,9 @@ def _two_chromosome_pos(path, pos_bp, cut):
             fh.write(f"{chrom}\t{pos}\n")
 
 
-def test_beagle_likelihoods_free_parameters(ours, tmp_path):
-    """BASELINE configs[0] style input; also the progress output, line for line."""
+@pytest.mark.parametrize("n_gpus", [1, 2, 3, 8])
+def test_beagle_likelihoods_free_parameters(ours, tmp_path, n_gpus):
+    """BASELINE configs[0] style input; also the progress output, line for line; one rank and sharded."""
     tmp = str(tmp_path)
     N, S = 8, 3000
     d = sim.simulate(N, S, seed=4242, freq=0.2, indF=0.5, alpha=0.01, depth=2.0)
@@ -97,7 +100,7 @@ def test_beagle_likelihoods_free_parameters(ours, tmp_path):
     sim.write_pos(os.path.join(tmp, "in.pos"), d.pos_bp)
     args = ["--geno", "in.beagle.gz", "--lkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "0.1",
             "--indF", "0.1,0.2", "--min_iters", "3", "--max_iters", "8", "--verbose", "3", "--n_threads", "4"]
-    pr, po = _both(ours, tmp, args)
+    pr, po = _both(ours, tmp, args, our_extra=["--n_gpus", str(n_gpus)])
     _same_files(tmp)
     assert _filtered(po.stdout) == _filtered(pr.stdout)
 
@@ -117,13 +120,14 @@ def test_binary_input_start_values_from_files(ours, tmp_path, fixed, freq_est):
             fh.write(f"{max(d.true_F[i], 1e-3):.6f}\t{d.true_alpha[i]:.6f}\n")
     args = ["--geno", "in.glf", "--loglkl", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "freq.txt",
             "--freq_est", freq_est, "--indF", "indF.txt", "--min_iters", "2", "--max_iters", "4", "--verbose", "1"] + fixed
-    pr, po = _both(ours, tmp, args)
+    pr, po = _both(ours, tmp, args, our_extra=["--n_gpus", "2"] if len(fixed) != 1 else [])
     _same_files(tmp)
     assert _filtered(po.stdout) == _filtered(pr.stdout)
 
 
+@pytest.mark.parametrize("n_gpus", [1, 3])
 @pytest.mark.parametrize("freq_est", ["0", "1"])
-def test_called_genotypes_and_estimated_start_frequencies(ours, tmp_path, freq_est):
+def test_called_genotypes_and_estimated_start_frequencies(ours, tmp_path, freq_est, n_gpus):
     """--freq e; with --freq_est 0 only the first site is estimated (parse_args.cpp:316-318)."""
     tmp = str(tmp_path)
     N, S = 6, 1500
@@ -132,7 +136,7 @@ def test_called_genotypes_and_estimated_start_frequencies(ours, tmp_path, freq_e
     sim.write_pos(os.path.join(tmp, "in.pos"), d.pos_bp)
     args = ["--geno", "in.geno.gz", "--n_ind", str(N), "--n_sites", str(S), "--pos", "in.pos", "--freq", "e", "--freq_est",
             freq_est, "--indF", "0.1,0.2", "--min_iters", "2", "--max_iters", "4", "--verbose", "0"]
-    _both(ours, tmp, args)
+    _both(ours, tmp, args, our_extra=["--n_gpus", str(n_gpus)])
     _same_files(tmp)
 
 
