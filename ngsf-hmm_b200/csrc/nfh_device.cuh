@@ -10,11 +10,12 @@
 // whole individual becomes a chunked associative scan.
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "nfh_math.cuh"
+#include "nfh_math.cuh"   // NFH_DEV; <cuda_runtime.h> under nvcc
+#if defined(__CUDACC__)
 #include "nfh_tma.cuh"
+#endif
 
 namespace nfh {
 
@@ -36,7 +37,7 @@ struct M2 {  // row-major [[a b] [c d]], acts on row vectors from the left: v' =
   double a, b, c, d;
 };
 
-__device__ __forceinline__ M2 matmul(const M2 &x, const M2 &y) {
+NFH_DEV M2 matmul(const M2 &x, const M2 &y) {
   M2 r;
   r.a = fma(x.a, y.a, x.b * y.c);
   r.b = fma(x.a, y.b, x.b * y.d);
@@ -46,28 +47,28 @@ __device__ __forceinline__ M2 matmul(const M2 &x, const M2 &y) {
 }
 
 // 2^e as a double, e clamped to the normal range.
-__device__ __forceinline__ double pow2i(int e) {
+NFH_DEV double pow2i(int e) {
   e = max(-1000, min(1000, e));
   return __hiloint2double((1023 + e) << 20, 0);
 }
 
 // Exponent (floor(log2)) of a non-negative double from its bit pattern;
 // 0 for zero/subnormal/inf/NaN so that those are left untouched.
-__device__ __forceinline__ int exponent_of(double m) {
+NFH_DEV int exponent_of(double m) {
   int be = (__double2hiint(m) >> 20) & 0x7ff;
   return (be == 0 || be == 0x7ff) ? 0 : max(-1000, min(1000, be - 1023));
 }
 
 // Scale a non-negative matrix so its largest entry lies in [1, 2); returns the
 // removed power of two (exact: multiplication by 2^-e does not round).
-__device__ __forceinline__ int renorm(M2 &m) {
+NFH_DEV int renorm(M2 &m) {
   int e = exponent_of(fmax(fmax(m.a, m.b), fmax(m.c, m.d)));
   double s = pow2i(-e);
   m.a *= s; m.b *= s; m.c *= s; m.d *= s;
   return e;
 }
 
-__device__ __forceinline__ int renorm2(double &x, double &y) {
+NFH_DEV int renorm2(double &x, double &y) {
   int e = exponent_of(fmax(x, y));
   double s = pow2i(-e);
   x *= s; y *= s;
@@ -78,18 +79,18 @@ __device__ __forceinline__ int renorm2(double &x, double &y) {
 // doubles the high words order like the values, so an IMNMX on them replaces the DSETP + selects of
 // fmax() (the FP64 pipe is the bottleneck of every recursion kernel).  NaN entries have the largest
 // high word and leave the scale untouched, as in renorm().
-__device__ __forceinline__ int exponent_of_hi(int hi) {
+NFH_DEV int exponent_of_hi(int hi) {
   const int be = (hi >> 20) & 0x7ff;
   return (be == 0 || be == 0x7ff) ? 0 : max(-1000, min(1000, be - 1023));
 }
-__device__ __forceinline__ int renorm_i(M2 &m) {
+NFH_DEV int renorm_i(M2 &m) {
   const int e = exponent_of_hi(max(max(__double2hiint(m.a), __double2hiint(m.b)),
                                    max(__double2hiint(m.c), __double2hiint(m.d))));
   const double s = pow2i(-e);
   m.a *= s; m.b *= s; m.c *= s; m.d *= s;
   return e;
 }
-__device__ __forceinline__ int renorm2_i(double &x, double &y) {
+NFH_DEV int renorm2_i(double &x, double &y) {
   const int e = exponent_of_hi(max(__double2hiint(x), __double2hiint(y)));
   const double s = pow2i(-e);
   x *= s; y *= s;
@@ -124,7 +125,7 @@ constexpr double kBigX = 76.24618986159398;           // 110 ln 2: largest expon
 enum : int { kTierFast = 0, kTierMid = 1, kTierSlow = 2 };
 constexpr double kFastX = 0.0054;
 constexpr double kMidX = 1.0;
-__device__ __forceinline__ int kappa_tier(double alpha_max, double tile_dmax) {
+NFH_DEV int kappa_tier(double alpha_max, double tile_dmax) {
   const double x = alpha_max * tile_dmax;               // NaN compares false twice -> slow tier
   return x < kFastX ? kTierFast : (x <= kMidX ? kTierMid : kTierSlow);
 }
@@ -132,7 +133,7 @@ __device__ __forceinline__ int kappa_tier(double alpha_max, double tile_dmax) {
 template <int TIER> struct TierTraits { static constexpr int kWindow = TIER == kTierSlow ? 4 : 8; };
 
 template <int TIER>
-__device__ __forceinline__ double tier_kappa(double x, const double *__restrict__ tab, double &log_scale) {
+NFH_DEV double tier_kappa(double x, const double *__restrict__ tab, double &log_scale) {
   if (TIER == kTierFast) return expm1_small(x);
   if (TIER == kTierMid) return expm1_pos(x, tab);
   const double xc = fmin(x, kBigX);
@@ -141,18 +142,18 @@ __device__ __forceinline__ double tier_kappa(double x, const double *__restrict_
 }
 
 // kappa for x = alpha * d; adds log c = -x (natural log) to log_scale.
-__device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab, double &log_scale) {
+NFH_DEV double site_kappa(double x, const double *__restrict__ tab, double &log_scale) {
   const double xc = fmin(x, kBigX);                   // fmin also maps NaN to the clamp
   log_scale -= xc;
   return expm1_pos(xc, tab);
 }
-__device__ __forceinline__ double site_kappa(double x, const double *__restrict__ tab) {
+NFH_DEV double site_kappa(double x, const double *__restrict__ tab) {
   return expm1_pos(fmin(x, kBigX), tab);
 }
 
 // M <- M * N_s with k0 = kappa q0, k1 = kappa q1:
 //   row (x0, x1) -> ( x0 + (x0+x1) k0 ,  (x1 + (x0+x1) k1) r )
-__device__ __forceinline__ void apply_site(M2 &m, double k0, double k1, double r) {
+NFH_DEV void apply_site(M2 &m, double k0, double k1, double r) {
   const double s0 = m.a + m.b, s1 = m.c + m.d;
   m.a = fma(s0, k0, m.a);
   m.b = fma(s0, k1, m.b) * r;
@@ -161,22 +162,23 @@ __device__ __forceinline__ void apply_site(M2 &m, double k0, double k1, double r
 }
 
 // row vector (a0, a1) <- (a0, a1) * N_s
-__device__ __forceinline__ void forward_site(double &a0, double &a1, double k0, double k1, double r) {
+NFH_DEV void forward_site(double &a0, double &a1, double k0, double k1, double r) {
   const double s = a0 + a1;
   a0 = fma(s, k0, a0);
   a1 = fma(s, k1, a1) * r;
 }
 
 // column vector (b0, b1) <- N_s * (b0, b1)
-__device__ __forceinline__ void backward_site(double &b0, double &b1, double k0, double k1, double r) {
+NFH_DEV void backward_site(double &b0, double &b1, double k0, double k1, double r) {
   const double w1 = r * b1;
   const double mix = fma(k0, b0, k1 * w1);
   b0 = b0 + mix;
   b1 = w1 + mix;
 }
 
-__device__ __forceinline__ M2 identity2() { M2 m; m.a = 1; m.b = 0; m.c = 0; m.d = 1; return m; }
+NFH_DEV M2 identity2() { M2 m; m.a = 1; m.b = 0; m.c = 0; m.d = 1; return m; }
 
+#if defined(__CUDACC__)   // warp-level pieces: device only
 __device__ __forceinline__ M2 shfl_down_m(const M2 &m, int off) {
   M2 r;
   r.a = __shfl_down_sync(kFull, m.a, off); r.b = __shfl_down_sync(kFull, m.b, off);
@@ -204,11 +206,12 @@ __device__ __forceinline__ void warp_ordered_product(M2 &m, int &e) {
     }
   }
 }
+#endif
 
 // Address of (individual row, site) in the site-blocked layout
 // [n_ranks][n_ind_local][site_block]; a tile never straddles a block because
 // site_block is a multiple of kTile.
-__device__ __forceinline__ size_t blocked_index(uint64_t row, uint64_t site, uint64_t n_rows, uint64_t site_block) {
+NFH_DEV size_t blocked_index(uint64_t row, uint64_t site, uint64_t n_rows, uint64_t site_block) {
   uint64_t blk = site / site_block;
   uint64_t off = site - blk * site_block;
   return (size_t) ((blk * n_rows + row) * site_block + off);

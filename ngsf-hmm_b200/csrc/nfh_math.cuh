@@ -10,7 +10,18 @@
 // so both are written without branches and with fewer FP64 instructions.
 #pragma once
 
+// NFH_DEV marks the pure-arithmetic device functions.  Under nvcc - the only way the product is built - it is
+// `__device__ __forceinline__` and nothing else changes.  tests/device_arith_host.cpp defines it (plus the four bit-cast
+// intrinsics and a stand-in for the hardware reciprocal seed) BEFORE including these headers and compiles the same
+// functions with g++, so that the CPU test suite checks the kernels' arithmetic against the reference's own arithmetic without a GPU.
+// That build is test infrastructure: no product code path reaches it.
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#define NFH_DEV __device__ __forceinline__
+#define NFH_DEV_TABLE __device__ const
+#elif !defined(NFH_DEV)
+#error "device header: build with nvcc (only tests/device_arith_host.cpp may predefine NFH_DEV)"
+#endif
 
 namespace nfh {
 
@@ -18,7 +29,7 @@ namespace nfh {
 // every CTA that calls expm1_pos().  Kept in global memory: the copy is one
 // coalesced load per thread, whereas per-lane indices into the constant bank
 // would serialise in the constant cache (and so would the lookups themselves).
-__device__ const double kExp2Table[64] = {
+NFH_DEV_TABLE double kExp2Table[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284, 1.0442737824274138, 1.0556451783605572,
     1.0671404006768237, 1.0787607977571199, 1.0905077326652577, 1.102382583307841, 1.1143867425958924,
     1.1265216186082418, 1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
@@ -33,14 +44,16 @@ __device__ const double kExp2Table[64] = {
     1.8539791250833855, 1.8741676341103, 1.8945759815869656, 1.9152065613971474, 1.9360617934922943,
     1.9571441241754002, 1.978456026387951};
 
+#if defined(__CUDACC__)
 __device__ __forceinline__ void load_exp_table(double *smem_tab) {
   if (threadIdx.x < 64) smem_tab[threadIdx.x] = kExp2Table[threadIdx.x];
 }
+#endif
 
 // kappa = e^x - 1 for 0 <= x <= 138 (caller guarantees the range), ~1 ulp of e^x.
 // x = k ln2/64 + r, e^x = 2^(k>>6) T[k&63] (1 + p(r)), |r| <= ln2/128.
 // 11 FP64 instructions + a shared-memory load; exact (= p) for x < ln2/128.
-__device__ __forceinline__ double expm1_pos(double x, const double *__restrict__ tab) {
+NFH_DEV double expm1_pos(double x, const double *__restrict__ tab) {
   const double kInv = 92.33248261689366;             // 64 / ln 2
   const double kMagic = 6755399441055744.0;              // 1.5 * 2^52
   const double kLn2_64_hi = 0.010830424696223417;  // ln2/64, top bits
@@ -62,7 +75,7 @@ __device__ __forceinline__ double expm1_pos(double x, const double *__restrict__
 
 // kappa = e^x - 1 for 0 <= x < 0.0054: the polynomial of expm1_pos() alone.  For such x expm1_pos() has
 // k = 0, r = x, table entry 1.0 and returns fma(1, p, 0) = p, so the two functions agree bit for bit.
-__device__ __forceinline__ double expm1_small(double x) {
+NFH_DEV double expm1_small(double x) {
   double p = fma(x, 1.0 / 120.0, 1.0 / 24.0);
   p = fma(p, x, 1.0 / 6.0);
   p = fma(p, x, 0.5);
@@ -74,16 +87,24 @@ __device__ __forceinline__ double expm1_small(double x) {
 // (y (1 + e + e^2), e = 1 - x y) -> error ~2^-69 before rounding, i.e. ~1 ulp.
 // With refine = true one more linear step is added (the full library sequence).
 // hardware reciprocal seed alone (relative error ~2^-23)
-__device__ __forceinline__ double rcp_seed(double x) {
+NFH_DEV double rcp_seed(double x) {
+#if defined(__CUDACC__)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   return y;
+#else
+  return nfh_host_rcp_seed(x);
+#endif
 }
 
 template <bool refine = false>
-__device__ __forceinline__ double rcp_pos(double x) {
+NFH_DEV double rcp_pos(double x) {
+#if defined(__CUDACC__)
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  double y = nfh_host_rcp_seed(x);
+#endif
   double e = fma(-x, y, 1.0);
   e = fma(e, e, e);
   y = fma(y, e, y);

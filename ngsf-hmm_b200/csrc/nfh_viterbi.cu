@@ -33,6 +33,7 @@
 //   viterbi_tile_states    : per individual, state at the end of every tile (right to left)
 //   viterbi_chunk_trace    : state at the end of every chunk, then the 33-site traceback
 #include "nfh_device.cuh"
+#include "nfh_viterbi_math.cuh"
 #include "nfh_kernels.h"
 
 namespace nfh {
@@ -65,38 +66,6 @@ __device__ __forceinline__ void vit_stage(VitSmem &sm, const double *__restrict_
     tma_load_1d(sm.d, dist_tile, kTileBytes, &sm.bar);
   }
   mbar_wait(&sm.bar, 0);
-}
-
-// (max, x) product and helpers; entries are non-negative
-__device__ __forceinline__ M2 tropmul(const M2 &x, const M2 &y) {
-  M2 r;
-  r.a = fmax(x.a * y.a, x.b * y.c);
-  r.b = fmax(x.a * y.b, x.b * y.d);
-  r.c = fmax(x.c * y.a, x.d * y.c);
-  r.d = fmax(x.c * y.b, x.d * y.d);
-  return r;
-}
-
-struct SiteQ { double q00, q01, q10, q11; };
-
-// true 0->1 transition probability (1-c) q1 = kappa q1 / (1 + kappa); = q1 at chromosome starts
-__device__ __forceinline__ double trans01(double kap, double q1) { return kap * q1 * rcp_pos(1.0 + kap); }
-
-__device__ __forceinline__ SiteQ site_q(double kap, double q0, double q1, double e0, double r) {
-  const double k0 = kap * q0, k1 = kap * q1, e1 = e0 * r;
-  const double t01 = trans01(kap, q1);
-  SiteQ s;
-  s.q00 = (1.0 + k0) * e0;
-  s.q10 = k0 * e0;
-  s.q01 = s.q00 * t01 * e1;
-  s.q11 = fmax(s.q10 * t01, 1.0 + k1) * e1;
-  return s;
-}
-
-__device__ __forceinline__ void trop_apply(M2 &m, const SiteQ &s) {
-  const double a = fmax(m.a * s.q00, m.b * s.q10), b = fmax(m.a * s.q01, m.b * s.q11);
-  const double c = fmax(m.c * s.q00, m.d * s.q10), d = fmax(m.c * s.q01, m.d * s.q11);
-  m.a = a; m.b = b; m.c = c; m.d = d;
 }
 
 // ordered (max,x) product over the warp (lane 0 gets the total)
@@ -179,11 +148,6 @@ viterbi_tile_scores(ViterbiArgs A) {
     renorm2(v0, v1);
   }
   if (lane == 0) A.final_state[row] = v1 > v0 ? 1 : 0;           // array_max_pos: first maximum
-}
-
-// maps {0,1} -> {0,1} as 2 bits: bit x = image of x.  compose(f, g)(x) = f(g(x)).
-__device__ __forceinline__ unsigned map_compose(unsigned f, unsigned g) {
-  return ((f >> (g & 1u)) & 1u) | (((f >> ((g >> 1) & 1u)) & 1u) << 1);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -317,13 +281,7 @@ viterbi_chunk_trace(ViterbiArgs A) {
   __syncthreads();
   const int n_valid = vit_valid_sites(tile_first + (uint64_t) threadIdx.x * kChunk, A.n_sites);
   unsigned char *b = tile_bytes + threadIdx.x * kChunk;
-  unsigned state = end_state[threadIdx.x];
-#pragma unroll 3
-  for (int j = kChunk - 1; j >= 0; j--) {
-    const unsigned bits = b[j];
-    b[j] = (unsigned char) (j < n_valid ? state : 0u);
-    state = (bits >> state) & 1u;
-  }
+  vit_chunk_trace(b, n_valid, end_state[threadIdx.x]);
   fence_async_shared();
   __syncthreads();
   if (threadIdx.x == 0) {
