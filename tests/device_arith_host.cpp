@@ -176,7 +176,7 @@ int da_estep(uint64_t S, const double *ratio, const double *dist, double F, doub
 // renormalised every kBody sites, chunk products chained in order.  Returns -log-likelihood.
 // ---------------------------------------------------------------------------------------------------------------
 double da_neg_lkl(uint64_t S, const double *ratio, const double *dist, double F, double alpha, double loge0_sum) {
-  if (F != F || alpha != alpha || std::isinf(F) || std::isinf(alpha)) return 1e15;   // EM.cpp:453-456 via nfh_ctx.cu
+  if (F != F || alpha != alpha || std::isinf(F) || std::isinf(alpha)) return -1e15;   // EM.cpp:454-456, as nfh_ctx.cu
   const uint64_t n_chunks = (S + kChunk - 1) / kChunk;
   const double q0 = 1.0 - F, q1 = F;
   double x0 = q0, x1 = q1, ls = 0.0;

@@ -289,7 +289,7 @@ def test_objective_body_matches_oracle(oracle, dev):
             got = dev.neg_lkl(e[i], d.dist_mb, ff, aa)
             want = oracle.lkl(e[i], d.dist_mb, ff, aa)
             assert abs(got - want) <= LKL_RTOL * abs(want)
-    assert dev.neg_lkl(e[0], d.dist_mb, np.nan, 0.1) == 1e15               # EM.cpp:454-456: lkl() returns -(-1e15)
+    assert dev.neg_lkl(e[0], d.dist_mb, np.nan, 0.1) == -1e15              # EM.cpp:454-456
 
 
 # ---------------------------------------------------------------------------------------------------------------
