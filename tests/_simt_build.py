@@ -1,0 +1,126 @@
+"""TEST INFRASTRUCTURE: builds the product's CUDA kernels for the SIMT emulator (tests/simt/simt.h).
+
+The kernel sources are COPIED from ngsf-hmm_b200/csrc into a scratch directory and rewritten mechanically - every
+rewrite asserts that it found what it expected, so a change of the kernels that the rewrites no longer cover fails
+loudly instead of testing stale text:
+
+  * `kernel<<<grid, block, smem, stream>>>(args);`  ->  `simt::launch(grid, block, smem, [&]() { kernel(args); });`
+  * `extern __shared__ __align__(n) T name[];`       ->  `T *name = (T *) simt::dyn_smem();`
+  * the warp-level helpers of nfh_device.cuh / nfh_math.cuh that are guarded by `__CUDACC__` are switched on
+    (shuffles and `threadIdx` exist in the emulator); the inline-PTX reciprocal seed keeps its host stand-in
+  * `__shared__ alignas(n)` -> `alignas(n) __shared__` (`__shared__` is `static` here and ISO C++ wants that order)
+  * nfh_tma.cuh is not used: simt.h provides synchronous bulk copies and mbarriers of the same names
+  * nfh_estep.cu: the single-launch variant (`estep_fused`, opt-in, inline PTX acquire / release) is cut out
+
+Nothing else changes: the kernels' bodies, their launchers and their launch geometry are the product's text.
+"""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "ngsf-hmm_b200", "csrc")
+SIMT = os.path.join(ROOT, "tests", "simt")
+
+
+def _split_top_level(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def rewrite_launches(src):
+    """kernel<<<g, b, s, st>>>(args);  ->  simt::launch(...)"""
+    out, pos, n = "", 0, 0
+    while True:
+        i = src.find("<<<", pos)
+        if i < 0:
+            break
+        m = re.search(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*$", src[pos:i])
+        assert m, "no kernel name before <<<"
+        name_start = pos + m.start(1)
+        j = src.index(">>>", i)
+        cfg = _split_top_level(src[i + 3:j])
+        assert len(cfg) == 4, cfg
+        k = src.index("(", j)
+        depth, e = 0, k
+        for e in range(k, len(src)):
+            depth += src[e] == "("
+            depth -= src[e] == ")"
+            if depth == 0:
+                break
+        assert src[e + 1] == ";", src[e:e + 20]
+        args = src[k + 1:e]
+        out += src[pos:name_start]
+        out += (f"simt::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t) ({cfg[2]}), "
+                f"[&]() {{ {m.group(1)}({args}); }});")
+        pos = e + 2
+        n += 1
+    return out + src[pos:], n
+
+
+def rewrite_dyn_smem(src):
+    pat = re.compile(r"extern __shared__ __align__\(\d+\) (unsigned char|double) (\w+)\[\];")
+    return pat.subn(lambda m: f"{m.group(1)} *{m.group(2)} = reinterpret_cast<{m.group(1)} *>(simt::dyn_smem());", src)
+
+
+def _cut(src, begin, end, what):
+    a = src.index(begin)
+    b = src.index(end, a)
+    assert a < b, what
+    return src[:a] + src[b:]
+
+
+def transform(name, src):
+    if name == "nfh_math.cuh":
+        old = "#if defined(__CUDACC__)\n__device__ __forceinline__ void load_exp_table"
+        assert src.count(old) == 1
+        src = src.replace(old, "#if 1\n__device__ __forceinline__ void load_exp_table")
+    if name == "nfh_device.cuh":
+        old = "#if defined(__CUDACC__)   // warp-level pieces: device only"
+        assert src.count(old) == 1
+        src = src.replace(old, "#if 1")
+    if name == "nfh_estep.cu":
+        # the opt-in single-launch variant: inline PTX (acquire / release, bulk-copy groups); not emulated
+        src = _cut(src, "// ---------------------------------------------------------------------------\n// Single-launch E-step.",
+                   "// ---------------------------------------------------------------------------\n// host-side launchers",
+                   "estep_fused section")
+        src = _cut(src, "static long env_long(", "void launch_estep(", "launch_estep_fused")
+        old = "  if (launch_estep_fused(a, st)) return;\n"
+        assert src.count(old) == 1
+        src = src.replace(old, "")
+        assert "asm" not in re.sub(r"//[^\n]*", "", src)
+    if name.endswith(".cu"):
+        src = re.sub(r"__shared__ alignas\((\d+)\)", r"alignas(\1) __shared__", src)   # ISO order for `static`
+        src, n_launch = rewrite_launches(src)
+        src, n_smem = rewrite_dyn_smem(src)
+        expect = {"nfh_estep.cu": (3, 2), "nfh_lkl.cu": (2, 1), "nfh_viterbi.cu": (5, 2)}.get(name)
+        if expect:
+            assert (n_launch, n_smem) == expect, (name, n_launch, n_smem)
+    return src
+
+
+def build(scratch, flags=("-ffp-contract=off",)):
+    """Rewrites the kernel sources into `scratch`, compiles the harness; returns the shared library's path."""
+    os.makedirs(scratch, exist_ok=True)
+    for f in sorted(os.listdir(CSRC)):
+        if not f.endswith((".cu", ".cuh", ".h")) or f in ("nfh_tma.cuh", "nfh_ctx.cu", "nfh_freq.cu"):
+            continue
+        text = open(os.path.join(CSRC, f)).read()
+        open(os.path.join(scratch, f), "w").write(transform(f, text))
+    so = os.path.join(scratch, "libsimt_kernels.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+           "-Wno-unused-variable", "-Wno-unused-but-set-variable"] + list(flags) + \
+          ["-I", scratch, "-I", SIMT, "-I", os.path.join(ROOT, "include"), "-o", so,
+           os.path.join(ROOT, "tests", "simt_kernels_host.cpp"), os.path.join(SIMT, "simt.cpp")]
+    subprocess.check_call(cmd)
+    return so

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE: what `#include <cuda_runtime.h>` resolves to when the kernels are built for the SIMT emulator.
+#pragma once
+#include "simt.h"

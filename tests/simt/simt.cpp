@@ -1,0 +1,95 @@
+// simt.cpp - the fiber scheduler of tests/simt/simt.h (TEST INFRASTRUCTURE ONLY).
+#include "simt.h"
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace simt {
+
+static Cta g_cta;
+static unsigned long long g_launches = 0, g_switches = 0;
+alignas(1024) static unsigned char g_dyn_smem[256 * 1024];
+constexpr size_t kStackBytes = 256 * 1024;
+
+Cta &cta() { return g_cta; }
+unsigned char *dyn_smem() { return g_dyn_smem; }
+unsigned long long launches() { return g_launches; }
+unsigned long long switches() { return g_switches; }
+
+void yield() {
+  Cta &c = g_cta;
+  g_switches++;
+  swapcontext(&c.fibers[c.cur].ctx, &c.sched);
+}
+
+static void fiber_main() {
+  Cta &c = g_cta;
+  (*c.body)();
+  c.fibers[c.cur].done = true;
+  // an exited thread no longer takes part in barriers: release whoever waits for it
+  c.live--;
+  if (c.live && c.bar_arrived >= c.live) { c.bar_arrived = 0; c.bar_gen++; }
+  Cta::Warp &w = c.warps[c.cur >> 5];
+  w.live--;
+  if (w.live && w.arrived >= w.live) { w.arrived = 0; w.gen++; }
+  swapcontext(&c.fibers[c.cur].ctx, &c.sched);
+}
+
+static void set_thread(unsigned t) {
+  Cta &c = g_cta;
+  c.cur = t;
+  threadIdx.x = t % c.block.x;
+  threadIdx.y = (t / c.block.x) % c.block.y;
+  threadIdx.z = t / (c.block.x * c.block.y);
+}
+
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &kernel_call) {
+  Cta &c = g_cta;
+  const unsigned n = block.x * block.y * block.z;
+  if (n == 0 || n > 1024 || dyn_smem_bytes > sizeof(g_dyn_smem)) { std::fprintf(stderr, "simt: bad launch\n"); std::abort(); }
+  g_launches++;
+  if (c.stacks.size() < (size_t) n * kStackBytes) c.stacks.resize((size_t) n * kStackBytes);
+  c.fibers.resize(n);
+  c.n_threads = n;
+  c.block = block;
+  c.body = &kernel_call;
+  blockDim = block;
+  gridDim = grid;
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++) {
+        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+        c.live = n; c.bar_arrived = 0;
+        for (unsigned w = 0; w < (n + 31) / 32; w++) {
+          c.warps[w].live = std::min(32u, n - 32 * w);
+          c.warps[w].arrived = 0;
+        }
+        for (unsigned t = 0; t < n; t++) {
+          Fiber &f = c.fibers[t];
+          f.done = false;
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = c.stacks.data() + (size_t) t * kStackBytes;
+          f.ctx.uc_stack.ss_size = kStackBytes;
+          f.ctx.uc_link = nullptr;
+          makecontext(&f.ctx, fiber_main, 0);
+        }
+        unsigned remaining = n;
+        unsigned long long idle_rounds = 0;
+        while (remaining) {
+          const unsigned long long before = g_switches;
+          unsigned finished_now = 0;
+          for (unsigned t = 0; t < n; t++) {
+            if (c.fibers[t].done) continue;
+            set_thread(t);
+            swapcontext(&c.sched, &c.fibers[t].ctx);
+            if (c.fibers[t].done) { remaining--; finished_now++; }
+          }
+          // every live fiber yielded and nobody finished for a very long time: a deadlock (missed barrier) in the kernel
+          idle_rounds = finished_now ? 0 : idle_rounds + 1;
+          if (idle_rounds > 2000000ull) { std::fprintf(stderr, "simt: no progress in block (%u,%u) - deadlock?\n", bx, by); std::abort(); }
+          (void) before;
+        }
+      }
+}
+
+}  // namespace simt

@@ -1,0 +1,172 @@
+// simt.h - TEST INFRASTRUCTURE ONLY: a small SIMT emulator, enough CUDA to run the product's kernels on the host.
+//
+// tests/test_simt_kernels_cpu.py copies ngsf-hmm_b200/csrc/*.cu / *.cuh into a scratch directory, applies a handful
+// of mechanical rewrites (kernel<<<g, b, s, st>>>(args) -> simt::launch(...), `extern __shared__` arrays -> the
+// emulator's dynamic shared memory, the inline-PTX sections cut out) and compiles them with g++ against this header,
+// which stands in for <cuda_runtime.h>.  Every CUDA thread of a CTA is a fiber (ucontext); CTAs run one after the
+// other; __syncthreads, warp shuffles and votes are rendezvous points between fibers; the TMA bulk copies and
+// their mbarriers (nfh_tma.cuh) are synchronous memcpy plus a phase bit.  The CPU test suite thereby runs the
+// kernels' real control flow - tiles, chunk scans, carries, ordered warp products, launch geometry - against the
+// oracle without a GPU.  It is a checker: nothing under ngsf-hmm_b200/ includes, builds or loads it.
+#pragma once
+
+#include <ucontext.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+// ---- CUDA vocabulary ------------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__ static
+#define __align__(n) alignas(n)
+#define NFH_DEV static inline
+#define NFH_DEV_TABLE static const
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct double2 { double x, y; };
+struct alignas(16) double4 { double x, y, z, w; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+
+typedef void *cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+struct alignas(64) CUtensorMap { unsigned char opaque[128]; };
+
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
+
+using std::max;
+using std::min;
+
+static inline int __double2hiint(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int) (uint32_t) (b >> 32); }
+static inline int __double2loint(double x) { uint64_t b; std::memcpy(&b, &x, 8); return (int) (uint32_t) b; }
+static inline double __hiloint2double(int hi, int lo) {
+  const uint64_t b = ((uint64_t) (uint32_t) hi << 32) | (uint64_t) (uint32_t) lo;
+  double x; std::memcpy(&x, &b, 8); return x;
+}
+static inline long long __double_as_longlong(double x) { long long b; std::memcpy(&b, &x, 8); return b; }
+// stand-in for MUFU.RCP64H: a seed good to ~2^-20 (the hardware's is ~2^-23), see tests/device_arith_host.cpp
+static inline double nfh_host_rcp_seed(double x) {
+  const double y = 1.0 / __hiloint2double(__double2hiint(x), 0);
+  return __hiloint2double(__double2hiint(y), 0);
+}
+static inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+
+// ---- the emulator ---------------------------------------------------------------------------------------------
+namespace simt {
+
+struct Fiber {
+  ucontext_t ctx;
+  bool done = false;
+};
+
+struct Cta {
+  std::vector<Fiber> fibers;
+  std::vector<char> stacks;
+  ucontext_t sched;
+  unsigned n_threads = 0, cur = 0;
+  unsigned live = 0, bar_arrived = 0, bar_gen = 0;                 // __syncthreads
+  struct Warp { unsigned live = 0, arrived = 0, gen = 0; uint64_t slot[32]; } warps[32];
+  const std::function<void()> *body = nullptr;
+  dim3 block;
+};
+
+Cta &cta();
+unsigned char *dyn_smem();                                           // 256 KB, 1024-byte aligned
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &kernel_call);
+void yield();
+unsigned long long launches();                                       // kernels launched so far
+unsigned long long switches();                                       // fiber switches so far
+
+inline void syncthreads() {
+  Cta &c = cta();
+  const unsigned gen = c.bar_gen;
+  if (++c.bar_arrived >= c.live) { c.bar_arrived = 0; c.bar_gen++; return; }
+  while (c.bar_gen == gen) yield();
+}
+inline void syncwarp() {
+  Cta &c = cta();
+  Cta::Warp &w = c.warps[c.cur >> 5];
+  const unsigned gen = w.gen;
+  if (++w.arrived >= w.live) { w.arrived = 0; w.gen++; return; }
+  while (w.gen == gen) yield();
+}
+template <class T> inline T exchange(T v, int src_lane) {             // src_lane outside 0..31: keep the own value
+  static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+  Cta &c = cta();
+  Cta::Warp &w = c.warps[c.cur >> 5];
+  uint64_t bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  w.slot[c.cur & 31] = bits;
+  syncwarp();
+  T r = v;
+  if (src_lane >= 0 && src_lane < 32) std::memcpy(&r, &w.slot[src_lane], sizeof(T));
+  syncwarp();
+  return r;
+}
+
+}  // namespace simt
+
+static inline void __syncthreads() { simt::syncthreads(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { simt::syncwarp(); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return simt::exchange(v, src & 31); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) { return simt::exchange(v, (int) (threadIdx.x & 31) - (int) d); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int = 32) { return simt::exchange(v, (int) (threadIdx.x & 31) + (int) d); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return simt::exchange(v, (int) (threadIdx.x & 31) ^ m); }
+static inline int __any_sync(unsigned, int pred) {
+  simt::Cta &c = simt::cta();
+  simt::Cta::Warp &w = c.warps[c.cur >> 5];
+  w.slot[c.cur & 31] = pred ? 1 : 0;
+  simt::syncwarp();
+  int any = 0;
+  const unsigned base = (c.cur >> 5) * 32;
+  for (unsigned l = 0; l < 32 && base + l < c.n_threads; l++)
+    if (!c.fibers[base + l].done && w.slot[l]) any = 1;
+  simt::syncwarp();
+  return any;
+}
+
+// ---- nfh_tma.cuh on the host: bulk copies are synchronous, an mbarrier is (phase << 63) | pending bytes -----------
+namespace nfh {
+static inline void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) { *bar += bytes; }
+static inline void mbar_complete_tx(uint64_t *bar, uint32_t bytes) {
+  if ((*bar & 0x7fffffffffffffffull) < bytes) { std::fprintf(stderr, "simt: mbarrier completes more bytes than expected\n"); std::abort(); }
+  *bar -= bytes;
+  if ((*bar & 0x7fffffffffffffffull) == 0) *bar ^= 0x8000000000000000ull;       // phase completes
+}
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) { while ((uint32_t) (*bar >> 63) == parity) simt::yield(); }
+static inline void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  if (bytes % 16 || ((uintptr_t) smem_dst | (uintptr_t) gmem_src) % 16) { std::fprintf(stderr, "simt: misaligned bulk copy\n"); std::abort(); }
+  std::memcpy(smem_dst, gmem_src, bytes);
+  mbar_complete_tx(bar, bytes);
+}
+static inline void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+  if (bytes % 16 || ((uintptr_t) smem_src | (uintptr_t) gmem_dst) % 16) { std::fprintf(stderr, "simt: misaligned bulk store\n"); std::abort(); }
+  std::memcpy(gmem_dst, smem_src, bytes);
+}
+static inline void tma_store_wait_read() {}
+static inline void fence_async_shared() {}
+}  // namespace nfh
