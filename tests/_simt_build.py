@@ -10,6 +10,9 @@ loudly instead of testing stale text:
     (shuffles and `threadIdx` exist in the emulator); the inline-PTX reciprocal seed keeps its host stand-in
   * `__shared__ alignas(n)` -> `alignas(n) __shared__` (`__shared__` is `static` here and ISO C++ wants that order)
   * nfh_tma.cuh is not used: simt.h provides synchronous bulk copies and mbarriers of the same names
+  * nfh_freq.cu: the named barrier of the team kernel (`bar.sync id, n`, inline PTX) -> simt::named_barrier; the FP64
+    probe of bench.py is cut; the tensor maps are encoded by the product's own freq_tensor_maps() through an emulated
+    cuTensorMapEncodeTiled and honoured by the emulator's tma_load_2d (box, out-of-bounds zero fill, swizzle)
   * nfh_estep.cu: the single-launch variant (`estep_fused`, opt-in, inline PTX acquire / release) is cut out
 
 Nothing else changes: the kernels' bodies, their launchers and their launch geometry are the product's text.
@@ -99,11 +102,19 @@ def transform(name, src):
         assert src.count(old) == 1
         src = src.replace(old, "")
         assert "asm" not in re.sub(r"//[^\n]*", "", src)
+    if name == "nfh_freq.cu":
+        old = 'asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(n_threads) : "memory");'
+        assert src.count(old) == 1
+        src = src.replace(old, "simt::named_barrier(team + 1, n_threads);")
+        # the FP64 probe of bench.py: events and device allocation, nothing to check on the host
+        a = src.index("double launch_fp64_probe(")
+        src = src[:a] + "}  // namespace nfh\n"
+        assert "asm" not in re.sub(r"//[^\n]*", "", src)
     if name.endswith(".cu"):
         src = re.sub(r"__shared__ alignas\((\d+)\)", r"alignas(\1) __shared__", src)   # ISO order for `static`
         src, n_launch = rewrite_launches(src)
         src, n_smem = rewrite_dyn_smem(src)
-        expect = {"nfh_estep.cu": (3, 2), "nfh_lkl.cu": (2, 1), "nfh_viterbi.cu": (5, 2)}.get(name)
+        expect = {"nfh_estep.cu": (3, 2), "nfh_lkl.cu": (2, 1), "nfh_viterbi.cu": (5, 2), "nfh_freq.cu": (11, 3)}.get(name)
         if expect:
             assert (n_launch, n_smem) == expect, (name, n_launch, n_smem)
     return src
@@ -113,12 +124,12 @@ def build(scratch, flags=("-ffp-contract=off",)):
     """Rewrites the kernel sources into `scratch`, compiles the harness; returns the shared library's path."""
     os.makedirs(scratch, exist_ok=True)
     for f in sorted(os.listdir(CSRC)):
-        if not f.endswith((".cu", ".cuh", ".h")) or f in ("nfh_tma.cuh", "nfh_ctx.cu", "nfh_freq.cu"):
+        if not f.endswith((".cu", ".cuh", ".h")) or f in ("nfh_tma.cuh", "nfh_ctx.cu"):
             continue
         text = open(os.path.join(CSRC, f)).read()
         open(os.path.join(scratch, f), "w").write(transform(f, text))
     so = os.path.join(scratch, "libsimt_kernels.so")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+    cmd = ["g++", "-O0", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
            "-Wno-unused-variable", "-Wno-unused-but-set-variable"] + list(flags) + \
           ["-I", scratch, "-I", SIMT, "-I", os.path.join(ROOT, "include"), "-o", so,
            os.path.join(ROOT, "tests", "simt_kernels_host.cpp"), os.path.join(SIMT, "simt.cpp")]

@@ -50,7 +50,54 @@ enum { cudaSuccess = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
-struct alignas(64) CUtensorMap { unsigned char opaque[128]; };
+
+// ---- the slice of the driver API behind freq_tensor_maps() (nfh_freq.cu): cuTensorMapEncodeTiled, fetched through
+// cudaGetDriverEntryPoint.  The "tensor map" records what the product asked for; tma_load_2d() below honours it.
+typedef uint32_t cuuint32_t;
+typedef uint64_t cuuint64_t;
+typedef int CUresult;
+enum { CUDA_SUCCESS = 0 };
+enum CUtensorMapDataType { CU_TENSOR_MAP_DATA_TYPE_FLOAT64 = 9 };
+enum CUtensorMapInterleave { CU_TENSOR_MAP_INTERLEAVE_NONE = 0 };
+enum CUtensorMapSwizzle { CU_TENSOR_MAP_SWIZZLE_NONE = 0, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_128B };
+enum CUtensorMapL2promotion { CU_TENSOR_MAP_L2_PROMOTION_NONE = 0 };
+enum CUtensorMapFloatOOBfill { CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE = 0 };
+struct alignas(64) CUtensorMap {
+  const unsigned char *base;
+  uint64_t dim[2];          // elements, innermost first
+  uint64_t row_stride;      // bytes between rows
+  uint32_t box[2];          // elements, innermost first
+  uint32_t swizzle_span;    // bytes: 0, 32, 64, 128
+  uint32_t elem_bytes;
+  unsigned char pad_[128 - 56];
+};
+static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+static inline CUresult simt_cuTensorMapEncodeTiled(CUtensorMap *m, CUtensorMapDataType dt, cuuint32_t rank, void *base,
+                                                   const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box,
+                                                   const cuuint32_t *estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  // the driver's own checks that matter for these maps
+  if (dt != CU_TENSOR_MAP_DATA_TYPE_FLOAT64 || rank != 2 || il != CU_TENSOR_MAP_INTERLEAVE_NONE) return 1;
+  if (((uintptr_t) base) % 16 || strides[0] % 16 || estr[0] != 1 || estr[1] != 1) return 1;
+  if (box[0] == 0 || box[1] == 0 || box[0] > 256 || box[1] > 256) return 1;
+  const uint32_t span = sw == CU_TENSOR_MAP_SWIZZLE_128B ? 128 : sw == CU_TENSOR_MAP_SWIZZLE_64B ? 64 : sw == CU_TENSOR_MAP_SWIZZLE_32B ? 32 : 0;
+  if (span && box[0] * 8 > span) return 1;              // the inner box dimension must fit the swizzle span
+  m->base = (const unsigned char *) base;
+  m->dim[0] = dims[0]; m->dim[1] = dims[1];
+  m->row_stride = strides[0];
+  m->box[0] = box[0]; m->box[1] = box[1];
+  m->swizzle_span = span;
+  m->elem_bytes = 8;
+  return CUDA_SUCCESS;
+}
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0, cudaDriverEntryPointSymbolNotFound = 1 };
+enum { cudaEnableDefault = 0 };
+static inline cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, int, cudaDriverEntryPointQueryResult *q) {
+  const bool ok = std::strcmp(name, "cuTensorMapEncodeTiled") == 0;
+  *fn = ok ? (void *) &simt_cuTensorMapEncodeTiled : nullptr;
+  *q = ok ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return cudaSuccess;
+}
 
 extern uint3 threadIdx, blockIdx;
 extern dim3 blockDim, gridDim;
@@ -112,6 +159,14 @@ inline void syncwarp() {
   if (++w.arrived >= w.live) { w.arrived = 0; w.gen++; return; }
   while (w.gen == gen) yield();
 }
+inline void named_barrier(int id, int n_threads) {                       // bar.sync id, n_threads
+  struct Named { int arrived = 0; unsigned gen = 0; };
+  static Named bars[16];
+  Named &b = bars[id & 15];
+  const unsigned gen = b.gen;
+  if (++b.arrived >= n_threads) { b.arrived = 0; b.gen++; return; }
+  while (b.gen == gen) yield();
+}
 template <class T> inline T exchange(T v, int src_lane) {             // src_lane outside 0..31: keep the own value
   static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
   Cta &c = cta();
@@ -162,6 +217,27 @@ static inline void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t by
   if (bytes % 16 || ((uintptr_t) smem_dst | (uintptr_t) gmem_src) % 16) { std::fprintf(stderr, "simt: misaligned bulk copy\n"); std::abort(); }
   std::memcpy(smem_dst, gmem_src, bytes);
   mbar_complete_tx(bar, bytes);
+}
+// box of box[1] rows x box[0] elements at element coordinates (x, y); out-of-bounds elements read as zero; with a
+// swizzle span the 16-byte chunk index inside each span-sized row is XORed with the row index modulo the number of
+// chunks (CU_TENSOR_MAP_SWIZZLE_32B / 64B / 128B for spans that equal the box row, as these maps use them)
+static inline void tma_load_2d(void *smem_dst, const void *tensor_map, int x, int y, uint64_t *bar) {
+  const CUtensorMap &m = *reinterpret_cast<const CUtensorMap *>(tensor_map);
+  const uint32_t row_bytes = m.box[0] * m.elem_bytes;
+  const uint32_t mask = m.swizzle_span ? m.swizzle_span / 16 - 1 : 0;
+  if (m.swizzle_span && ((uintptr_t) smem_dst) % (8 * m.swizzle_span)) { std::fprintf(stderr, "simt: swizzled box not aligned to its pattern\n"); std::abort(); }
+  unsigned char *dst = reinterpret_cast<unsigned char *>(smem_dst);
+  for (uint32_t r = 0; r < m.box[1]; r++)
+    for (uint32_t c = 0; c < m.box[0]; c++) {
+      uint32_t off = r * row_bytes + c * m.elem_bytes;
+      off ^= ((off >> 7) & mask) << 4;
+      const int64_t gx = (int64_t) x + c, gy = (int64_t) y + r;
+      double v = 0.0;
+      if (gx >= 0 && gy >= 0 && (uint64_t) gx < m.dim[0] && (uint64_t) gy < m.dim[1])
+        std::memcpy(&v, m.base + (uint64_t) gy * m.row_stride + (uint64_t) gx * m.elem_bytes, 8);
+      std::memcpy(dst + off, &v, 8);
+    }
+  mbar_complete_tx(bar, m.box[1] * row_bytes);
 }
 static inline void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
   if (bytes % 16 || ((uintptr_t) smem_src | (uintptr_t) gmem_dst) % 16) { std::fprintf(stderr, "simt: misaligned bulk store\n"); std::abort(); }

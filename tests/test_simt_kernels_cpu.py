@@ -1,5 +1,5 @@
 """CPU: the product's CUDA KERNELS THEMSELVES - `__global__` functions, launchers and launch geometry of nfh_estep.cu,
-nfh_lkl.cu and nfh_viterbi.cu - run under a small SIMT emulator (tests/simt/simt.h: every CUDA thread a fiber,
+nfh_lkl.cu, nfh_viterbi.cu and nfh_freq.cu - run under a small SIMT emulator (tests/simt/simt.h: every CUDA thread a fiber,
 `__syncthreads` / shuffles / votes as rendezvous, TMA bulk copies + mbarriers as synchronous copies with a phase bit)
 and meet the oracle at the north star's tolerances.  tests/_simt_build.py copies the kernel sources and rewrites only
 what a host compiler cannot read (`<<<...>>>`, `extern __shared__`, the `__CUDACC__` guards of the warp helpers); every
@@ -8,7 +8,7 @@ chunk boundaries, warp scans and ordered products, the carry kernels, padding of
 objective points, back-pointer maps across chunks and tiles.
 
 It is a checker, not a code path: nothing under ngsf-hmm_b200/ knows about it, and the real kernels still need a
-B200 (`-m gpu` runs the same comparisons on the hardware, plus the frequency kernels and the C ABI around them).
+B200 (`-m gpu` runs the same comparisons on the hardware, through the C ABI, at sizes an emulator cannot reach).
 """
 import ctypes as C
 
@@ -40,6 +40,17 @@ class SimtKernels:
         L.simt_lkl_batch.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), _dp, _dp, _dp, C.c_int, _dp, _dp]
         L.simt_viterbi.argtypes = [C.c_void_p, C.c_void_p]
         L.simt_counters.argtypes = [C.POINTER(C.c_ulonglong)]
+        L.simt_freq_create.restype = C.c_void_p
+        L.simt_freq_create.argtypes = [C.c_uint64, C.c_uint64, _dp, C.c_int]
+        L.simt_freq_destroy.argtypes = [C.c_void_p]
+        L.simt_freq_set.argtypes = [C.c_void_p, _dp, _dp]
+        L.simt_freq_get_gl.argtypes = [C.c_void_p, _dp]
+        L.simt_freq_run.restype = C.c_int
+        L.simt_freq_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp,
+                                    C.POINTER(C.c_ulonglong)]
+        L.simt_geno_posterior.argtypes = [C.c_void_p, C.c_void_p, _dp]
+        L.simt_freq_run_stream.restype = C.c_int
+        L.simt_freq_run_stream.argtypes = [C.c_void_p, C.c_int, C.c_uint, _dp, _dp, _dp, C.POINTER(C.c_ulonglong)]
 
     def counters(self):
         c = (C.c_ulonglong * 2)()
@@ -89,6 +100,53 @@ class Ctx:
         path = np.zeros((self.N, self.S), dtype=np.uint8)
         self.L.simt_viterbi(self.h, path.ctypes.data)
         return path.astype(np.int8)
+
+
+class FreqSide:
+    """The frequency side of one rank (run_freq_family of nfh_ctx.cu) from normalised log GL (N,S,3)."""
+
+    def __init__(self, k, gl_ind, sm_count=2):
+        self.L = k.lib
+        g = np.ascontiguousarray(np.transpose(gl_ind, (1, 0, 2)), dtype=np.float64)     # [S][N][3] as nfh_upload_gl
+        self.N, self.S = gl_ind.shape[0], gl_ind.shape[1]
+        self.h = self.L.simt_freq_create(self.N, self.S, _p(g), sm_count)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.L.simt_freq_destroy(self.h)
+
+    def run(self, post=None, freq=None, update=True, prefetch=True, with_e0=True):
+        """-> dict(freq, ratio, e0, loge0, passes, code, prefetched)"""
+        p = np.ascontiguousarray(post, dtype=np.float64) if post is not None else None
+        f = np.ascontiguousarray(freq, dtype=np.float64) if freq is not None else None
+        self.L.simt_freq_set(self.h, _p(p), _p(f))
+        fr, ratio, e0, l0 = np.empty(self.S), np.empty((self.N, self.S)), np.empty((self.N, self.S)), np.empty(self.N)
+        used, passes = C.c_int(), C.c_ulonglong()
+        code = self.L.simt_freq_run(self.h, int(update), int(post is None), int(with_e0), int(prefetch), C.byref(used),
+                                    _p(fr), _p(ratio), _p(e0), _p(l0), C.byref(passes))
+        assert code > 0
+        return dict(freq=fr, ratio=ratio, e0=e0, loge0=l0, passes=passes.value, code=code, prefetched=bool(used.value))
+
+    def run_stream(self, post, chunks=3):
+        self.L.simt_freq_set(self.h, _p(np.ascontiguousarray(post, dtype=np.float64)), None)
+        fr, ratio, l0 = np.empty(self.S), np.empty((self.N, self.S)), np.empty(self.N)
+        passes = C.c_ulonglong()
+        code = self.L.simt_freq_run_stream(self.h, 1, chunks, _p(fr), _p(ratio), _p(l0), C.byref(passes))
+        assert code == 2
+        return dict(freq=fr, ratio=ratio, loge0=l0, passes=passes.value)
+
+    def linear_gl(self):
+        out = np.empty((3, self.N, self.S))
+        self.L.simt_freq_get_gl(self.h, _p(out))
+        return out
+
+    def geno_posterior(self, path):
+        p = np.ascontiguousarray(path, dtype=np.int8)
+        out = np.empty((self.S, self.N, 3))
+        self.L.simt_geno_posterior(self.h, p.ctypes.data, _p(out))
+        return out
 
 
 @pytest.fixture(scope="module")
@@ -280,6 +338,153 @@ def test_viterbi_kernels_breaks_and_hard_calls(oracle, kernels):
     for i in range(3):
         assert (oracle.viterbi(e[i], dist, 0.3, 0.2)[1] != path[i]).sum() == 0
         assert (path[i][geno[i] == 1] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# gl_ingest, freq_emission_{warp,hybrid,team,stream}, reduce_loge0 through freq_tensor_maps / freq_grid_size /
+# launch_freq_emission: the product picks the kernel shape; two "SMs" so that every CTA walks several site tiles
+# ---------------------------------------------------------------------------------------------------------------
+def _freq_case(oracle, N, S, seed):
+    d = sim.simulate(N, S, seed=seed, freq=(0.02, 0.5), indF=(0.0, 0.5))
+    gl_ind = oracle.normalize_gl(np.transpose(d.log_gl, (1, 0, 2)))
+    rng = np.random.default_rng(seed)
+    post = np.where(rng.random((N, S)) < 0.3, rng.choice([0.0, 1.0], (N, S)), rng.random((N, S)))
+    return gl_ind, post
+
+
+def _check_freq(oracle, gl_ind, post, got, freq0=None):
+    N, S = gl_ind.shape[:2]
+    zero = np.zeros((N, S))
+    f_o, e_o = oracle.freq_emission(gl_ind, post if post is not None else zero,
+                                    freq0 if freq0 is not None else np.full(S, 0.1), update_freq=freq0 is None)
+    np.testing.assert_allclose(got["freq"], f_o, rtol=0, atol=1e-11)
+    if freq0 is None:
+        want = sum(oracle.est_maf_counted(gl_ind[:, s, :], (post if post is not None else zero)[:, s])[1] for s in range(S))
+        assert got["passes"] == want                                          # nfh_freq_passes: bench.py's work figure
+    np.testing.assert_allclose(np.log(got["e0"]), e_o[:, :, 0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.log(got["ratio"]), e_o[:, :, 1] - e_o[:, :, 0], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(got["loge0"], e_o[:, :, 0].sum(axis=1), rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("N,S,prefetch", [(20, 150, True), (20, 150, False), (100, 90, True), (6, 70, True), (13, 33, True),
+                                          (125, 50, True), (200, 40, True), (450, 20, True), (37, 1, True)],
+                         ids=["G4-K5", "G4-K5-no-prefetch", "G8-K13-configs1", "G4-K2", "G4-K4", "G16-K8-configs2",
+                              "G16-K13-global-acc", "G32-K15-global-acc", "one-site"])
+def test_frequency_kernels_lane_group_shapes(oracle, kernels, N, S, prefetch):
+    """freq_emission_warp<G, K, MODE>: tile prefetch by 2-D tensor copies into swizzled double buffers (mbarrier phases
+    over several tiles per CTA) or plain loads; log e0 accumulators in shared memory or global scratch."""
+    gl_ind, post = _freq_case(oracle, N, S, 21 + N)
+    with FreqSide(kernels, gl_ind) as fs:
+        if N == 20:
+            np.testing.assert_allclose(fs.linear_gl(), np.exp(np.transpose(gl_ind, (2, 0, 1))), rtol=4e-16)   # gl_ingest
+        got = fs.run(post=post, prefetch=prefetch)
+    assert got["code"] == 1 and got["prefetched"] == prefetch
+    _check_freq(oracle, gl_ind, post, got)
+
+
+@pytest.mark.parametrize("N,S,no_hybrid", [(600, 12, 0), (900, 8, 0), (1000, 8, 0), (600, 8, 1), (1100, 6, 0)],
+                         ids=["hybrid-K19", "hybrid-13+16", "hybrid-14+18", "team-W2", "team-W4"])
+def test_frequency_kernels_many_individuals(oracle, kernels, monkeypatch, N, S, no_hybrid):
+    """More individuals than one warp's registers hold (the frequency side of a multi-rank run sees all of them):
+    registers + shared-memory columns, teams of warps behind named barriers."""
+    if no_hybrid:
+        monkeypatch.setenv("NFH_FREQ_NO_HYBRID", "1")
+    gl_ind, post = _freq_case(oracle, N, S, 31)
+    with FreqSide(kernels, gl_ind) as fs:
+        got = fs.run(post=post)
+    assert got["code"] == 1
+    _check_freq(oracle, gl_ind, post, got)
+
+
+def test_frequency_streaming_kernels(oracle, kernels):
+    """freq_emission_stream + loge0_rowsum (any number of individuals, the reference's summation order).  The
+    launcher only takes this path beyond 4,096 individuals - (64 x n_ind) CTAs of loge0_rowsum, hours under an
+    emulator - so the two kernels are launched directly, with three row chunks."""
+    N, S = 50, 300
+    gl_ind, post = _freq_case(oracle, N, S, 33)
+    with FreqSide(kernels, gl_ind) as fs:
+        got = fs.run_stream(post, chunks=3)
+    f_o, e_o = oracle.freq_emission(gl_ind, post, np.full(S, 0.1), update_freq=True)
+    np.testing.assert_allclose(got["freq"], f_o, rtol=0, atol=1e-11)
+    assert got["passes"] == sum(oracle.est_maf_counted(gl_ind[:, s, :], post[:, s])[1] for s in range(S))
+    np.testing.assert_allclose(np.log(got["ratio"]), e_o[:, :, 1] - e_o[:, :, 0], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(got["loge0"], e_o[:, :, 0].sum(axis=1), rtol=1e-12, atol=1e-10)
+
+
+def test_frequency_kernels_start_estimate_and_refresh_only(oracle, kernels):
+    """--freq e (posterior plane absent: F = 0, parse_args.cpp:316-318) and --freq_est 0 (frequencies kept)."""
+    N, S = 10, 120
+    gl_ind, post = _freq_case(oracle, N, S, 41)
+    with FreqSide(kernels, gl_ind) as fs:
+        _check_freq(oracle, gl_ind, None, fs.run(post=None))
+        fr = np.random.default_rng(41).uniform(0.01, 0.99, S)
+        got = fs.run(post=post, freq=fr, update=False)
+        np.testing.assert_array_equal(got["freq"], fr)
+        assert got["passes"] == 0
+        _check_freq(oracle, gl_ind, post, got, freq0=fr)
+
+
+def test_frequency_kernels_hard_calls_and_monomorphic_sites(oracle, kernels):
+    rng = np.random.default_rng(5)
+    N, S = 12, 96
+    geno = rng.integers(0, 3, size=(N, S))
+    geno[:, 0] = 0; geno[:, 1] = 2; geno[:, 2] = 1; geno[:, 3] = 2; geno[:6, 4] = 0; geno[6:, 4] = 2
+    geno[:, 40:48] = 2; geno[:, 60:64] = 0
+    gl = np.full((N, S, 3), -np.inf)
+    np.put_along_axis(gl, geno[:, :, None], 0.0, axis=2)
+    gl_ind = oracle.normalize_gl(gl)
+    post = np.where(rng.random((N, S)) < 0.5, 0.0, rng.random((N, S)))
+    post[geno == 1] = 0.0
+    with FreqSide(kernels, gl_ind) as fs:
+        got = fs.run(post=post, with_e0=False)
+    f_o, _ = oracle.freq_emission(gl_ind, post, np.full(S, 0.1), update_freq=True)
+    assert np.isfinite(got["freq"]).all() and np.isfinite(got["ratio"]).all()
+    np.testing.assert_allclose(got["freq"], f_o, rtol=0, atol=1e-11)
+    assert got["freq"][0] == 0.0 and abs(got["freq"][1] - 1.0) < 1e-15 and abs(got["freq"][2] - 0.5) < 1e-15
+
+
+def test_geno_posterior_kernel(oracle, kernels):
+    """.geno (EM.cpp:369-376): exp(post_prob(GL, HWE(freq, F = path)))."""
+    N, S = 5, 300
+    gl_ind, post = _freq_case(oracle, N, S, 71)
+    rng = np.random.default_rng(71)
+    fr = rng.uniform(0.02, 0.98, S)
+    path = (rng.random((N, S)) < 0.3).astype(np.int8)
+    with FreqSide(kernels, gl_ind) as fs:
+        fs.run(post=post, freq=fr, update=False)
+        got = fs.geno_posterior(path)
+    want = np.empty((S, N, 3))
+    for s in range(S):
+        for i in range(N):
+            pp = gl_ind[i, s] + oracle.calc_HWE(fr[s], float(path[i, s]), True)
+            m = pp.max(); pp = pp - (m + np.log(np.exp(pp - m).sum()))
+            want[s, i] = np.exp(pp)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+
+
+def test_one_em_iteration_of_kernels(oracle, kernels):
+    """E-step kernels -> frequency kernels -> E-step kernels on the refreshed emissions (ratio + sum of log e0), as
+    tests/test_gpu_parity.py::test_freq_update_matches_oracle chains them on the GPU."""
+    N, S = 6, 3000
+    d = sim.simulate(N, S, seed=21, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    gl_ind = oracle.normalize_gl(np.transpose(d.log_gl, (1, 0, 2)))
+    freq0 = np.full(S, 0.1); F = np.full(N, 0.1); a = np.full(N, 0.2)
+    _, e = oracle.freq_emission(gl_ind, None, freq0, update_freq=False)
+    with Ctx(kernels, e, d.dist_mb) as ctx:
+        ctx.set_params(F, a)
+        st, lk, post = ctx.estep()
+    with FreqSide(kernels, gl_ind) as fs:
+        got = fs.run(post=post)
+    f_o, e_o = oracle.freq_emission(gl_ind, post, freq0, update_freq=True)
+    np.testing.assert_allclose(got["freq"], f_o, rtol=0, atol=1e-11)
+    e_dev = np.stack([np.log(got["e0"]), np.log(got["e0"]) + np.log(got["ratio"])], axis=2)
+    with Ctx(kernels, e_dev, d.dist_mb) as ctx:
+        ctx.set_params(F, a)
+        st2, lk2, post2 = ctx.estep()
+    st_o, marg2, lk2_o = oracle.estep(e_o, d.dist_mb, F, a)
+    assert st == 0 and st2 == 0
+    np.testing.assert_allclose(lk2, lk2_o, rtol=LKL_RTOL)
+    _posterior_check(post2, marg2)
 
 
 def test_the_emulator_ran_threads_not_a_shortcut(kernels):
