@@ -487,6 +487,26 @@ def test_one_em_iteration_of_kernels(oracle, kernels):
     _posterior_check(post2, marg2)
 
 
-def test_the_emulator_ran_threads_not_a_shortcut(kernels):
-    launches, switches = kernels.counters()
-    assert launches >= 50 and switches > 1_000_000                            # fibers really met at barriers and shuffles
+def test_product_does_not_know_the_emulator():
+    """A checker, not a code path: nothing the product builds or loads mentions the emulator or its build."""
+    import os
+    import re
+    root = os.path.join(_simt_build.ROOT, "ngsf-hmm_b200")
+    for base, _, files in os.walk(root):
+        if os.sep + "build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".h", ".cu", ".cuh")) or f == "Makefile":
+                text = open(os.path.join(base, f), errors="replace").read()
+                assert not re.search(r"\bsimt\b|_simt_build|simt_kernels", text, re.I), os.path.join(base, f)
+
+
+def test_the_emulator_ran_threads_not_a_shortcut(oracle, kernels):
+    """One E-step of one tile = 3 launches and tens of thousands of fiber switches at barriers and shuffles."""
+    d, e = _case(oracle, 1, 500, 3, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    launches0, switches0 = kernels.counters()
+    with Ctx(kernels, e, d.dist_mb) as ctx:
+        ctx.set_params(np.array([0.2]), np.array([0.1]))
+        ctx.estep()
+    launches1, switches1 = kernels.counters()
+    assert launches1 - launches0 == 3 and switches1 - switches0 > 10_000
