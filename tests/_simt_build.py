@@ -120,18 +120,20 @@ def transform(name, src):
     return src
 
 
-def build(scratch, flags=("-ffp-contract=off",)):
-    """Rewrites the kernel sources into `scratch`, compiles the harness; returns the shared library's path."""
+def build(scratch, flags=("-ffp-contract=off",), extra_sources=(), extra_objects=(), name="libsimt_kernels.so"):
+    """Rewrites the kernel sources into `scratch`, compiles the harness (plus `extra_sources`, linked with
+    `extra_objects`); returns the shared library's path."""
     os.makedirs(scratch, exist_ok=True)
     for f in sorted(os.listdir(CSRC)):
         if not f.endswith((".cu", ".cuh", ".h")) or f in ("nfh_tma.cuh", "nfh_ctx.cu"):
             continue
         text = open(os.path.join(CSRC, f)).read()
         open(os.path.join(scratch, f), "w").write(transform(f, text))
-    so = os.path.join(scratch, "libsimt_kernels.so")
+    so = os.path.join(scratch, name)
     cmd = ["g++", "-O0", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
            "-Wno-unused-variable", "-Wno-unused-but-set-variable"] + list(flags) + \
           ["-I", scratch, "-I", SIMT, "-I", os.path.join(ROOT, "include"), "-o", so,
-           os.path.join(ROOT, "tests", "simt_kernels_host.cpp"), os.path.join(SIMT, "simt.cpp")]
+           os.path.join(ROOT, "tests", "simt_kernels_host.cpp"), os.path.join(SIMT, "simt.cpp")] + \
+          list(extra_sources) + list(extra_objects) + ["-Wl,--no-undefined"]
     subprocess.check_call(cmd)
     return so

@@ -4,6 +4,36 @@
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
+// Fiber switch.  swapcontext() makes a sigprocmask system call per switch, and an emulated EM run switches fibers a
+// few hundred million times; on x86-64 the switch is done by hand instead: push the callee-saved registers, swap the
+// stack pointers, pop, return.  Everything else (and any other architecture) uses ucontext.
+#if defined(__x86_64__) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_ASM_SWITCH 1
+extern "C" void simt_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch,@function
+simt_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size simt_switch,.-simt_switch
+)");
+#endif
+
 namespace simt {
 
 static Cta g_cta;
@@ -16,10 +46,26 @@ unsigned char *dyn_smem() { return g_dyn_smem; }
 unsigned long long launches() { return g_launches; }
 unsigned long long switches() { return g_switches; }
 
-void yield() {
+static inline void to_scheduler() {
   Cta &c = g_cta;
-  g_switches++;
+#ifdef SIMT_ASM_SWITCH
+  simt_switch(&c.fibers[c.cur].sp, c.sched_sp);
+#else
   swapcontext(&c.fibers[c.cur].ctx, &c.sched);
+#endif
+}
+static inline void to_fiber(unsigned t) {
+  Cta &c = g_cta;
+#ifdef SIMT_ASM_SWITCH
+  simt_switch(&c.sched_sp, c.fibers[t].sp);
+#else
+  swapcontext(&c.sched, &c.fibers[t].ctx);
+#endif
+}
+
+void yield() {
+  g_switches++;
+  to_scheduler();
 }
 
 static void fiber_main() {
@@ -32,7 +78,7 @@ static void fiber_main() {
   Cta::Warp &w = c.warps[c.cur >> 5];
   w.live--;
   if (w.live && w.arrived >= w.live) { w.arrived = 0; w.gen++; }
-  swapcontext(&c.fibers[c.cur].ctx, &c.sched);
+  for (;;) to_scheduler();                 // never resumed; never returns
 }
 
 static void set_thread(unsigned t) {
@@ -67,11 +113,22 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
         for (unsigned t = 0; t < n; t++) {
           Fiber &f = c.fibers[t];
           f.done = false;
+#ifdef SIMT_ASM_SWITCH
+          // initial frame: six callee-saved registers, the entry point as return address; after the pops and the
+          // `ret` the stack pointer is 8 modulo 16, as at any function entry
+          uintptr_t top = (uintptr_t) (c.stacks.data() + (size_t) (t + 1) * kStackBytes) & ~(uintptr_t) 15;
+          void **frame = reinterpret_cast<void **>(top - 64);
+          for (int k = 0; k < 6; k++) frame[k] = nullptr;
+          frame[6] = (void *) &fiber_main;
+          frame[7] = nullptr;
+          f.sp = frame;
+#else
           getcontext(&f.ctx);
           f.ctx.uc_stack.ss_sp = c.stacks.data() + (size_t) t * kStackBytes;
           f.ctx.uc_stack.ss_size = kStackBytes;
           f.ctx.uc_link = nullptr;
           makecontext(&f.ctx, fiber_main, 0);
+#endif
         }
         unsigned remaining = n;
         unsigned long long idle_rounds = 0;
@@ -81,7 +138,7 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
           for (unsigned t = 0; t < n; t++) {
             if (c.fibers[t].done) continue;
             set_thread(t);
-            swapcontext(&c.sched, &c.fibers[t].ctx);
+            to_fiber(t);
             if (c.fibers[t].done) { remaining--; finished_now++; }
           }
           // every live fiber yielded and nobody finished for a very long time: a deadlock (missed barrier) in the kernel

@@ -124,7 +124,8 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 namespace simt {
 
 struct Fiber {
-  ucontext_t ctx;
+  ucontext_t ctx;        // portable path
+  void *sp = nullptr;    // x86-64 path: saved stack pointer (callee-saved registers live on the fiber's stack)
   bool done = false;
 };
 
@@ -132,6 +133,7 @@ struct Cta {
   std::vector<Fiber> fibers;
   std::vector<char> stacks;
   ucontext_t sched;
+  void *sched_sp = nullptr;
   unsigned n_threads = 0, cur = 0;
   unsigned live = 0, bar_arrived = 0, bar_gen = 0;                 // __syncthreads
   struct Warp { unsigned live = 0, arrived = 0, gen = 0; uint64_t slot[32]; } warps[32];

@@ -89,6 +89,14 @@ SimtCtx *simt_create(uint64_t N, uint64_t S, const double *ratio, const double *
   return c;
 }
 void simt_destroy(SimtCtx *c) { delete c; }
+// refreshed emissions (after a frequency update): ratio / e0 [N][S], loge0_sum [N]
+void simt_update_emissions(SimtCtx *c, const double *ratio, const double *e0, const double *loge0_sum) {
+  for (uint64_t i = 0; i < c->N; i++) {
+    std::memcpy(&c->emis[i * c->S_pad], ratio + i * c->S, c->S * sizeof(double));
+    if (e0) std::memcpy(&c->e0[i * c->S_pad], e0 + i * c->S, c->S * sizeof(double));
+  }
+  c->loge0.assign(loge0_sum, loge0_sum + c->N);
+}
 void simt_set_params(SimtCtx *c, const double *F, const double *alpha) {
   c->indF.assign(F, F + c->N);
   c->alpha.assign(alpha, alpha + c->N);

@@ -1,7 +1,8 @@
 """CPU: whole EM iterations and whole EM runs of the PRODUCT - its host library compiled as it is (host/lbfgsb.cpp,
 bfgs_driver.cpp, host_api.cpp) over a fake device that computes with the KERNELS' OWN ARITHMETIC
 (tests/fake_device_arith.cpp on tests/device_arith_host.cpp: the per-thread bodies of the CUDA kernels compiled for
-the host) - against the golden fixtures generated from the unmodified reference (tests/golden/make_golden*.py) and
+the host) and over one that runs the KERNELS THEMSELVES under the SIMT emulator (tests/fake_device_simt.cpp on
+tests/simt_kernels_host.cpp: global functions, launchers, launch geometry) - against the golden fixtures generated from the unmodified reference (tests/golden/make_golden*.py) and
 against the reference itself (oracle/_ref), at the north star's tolerances: log-likelihood 1e-9 relative, posterior
 1e-8 absolute, F / alpha / frequencies 1e-6 after full EM, identical Viterbi tracts.
 
@@ -28,8 +29,10 @@ dp = C.POINTER(C.c_double)
 ITER_CASES = sorted(glob.glob(os.path.join(HERE, "golden", "iter_*.npz")))
 
 
-@pytest.fixture(scope="module")
-def lib(tmp_path_factory):
+@pytest.fixture(scope="module", params=["kernel-arithmetic", "kernels-under-emulator"])
+def lib(request, tmp_path_factory):
+    """The product's host library over (a) tests/fake_device_arith.cpp: the kernels' per-thread arithmetic strung
+    together sequentially, or (b) tests/fake_device_simt.cpp: the kernels themselves under the SIMT emulator."""
     d = str(tmp_path_factory.mktemp("host_on_device_arith"))
     inc = ["-I", os.path.join(ROOT, "include"), "-I", HOST, "-I", CSRC]
     objs = []
@@ -38,22 +41,28 @@ def lib(tmp_path_factory):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"] + inc +
                               ["-c", os.path.join(HOST, src), "-o", o])
         objs.append(o)
-    for src in ("device_arith_host.cpp", "fake_device_arith.cpp"):
-        o = os.path.join(d, src + ".o")
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas"] + inc +
-                              ["-c", os.path.join(ROOT, "tests", src), "-o", o])
-        objs.append(o)
-    so = os.path.join(d, "libhost_on_device_arith.so")
-    subprocess.check_call(["g++", "-shared", "-o", so] + objs + ["-Wl,--no-undefined"])
+    o = os.path.join(d, "device_arith_host.cpp.o")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas"] + inc +
+                          ["-c", os.path.join(ROOT, "tests", "device_arith_host.cpp"), "-o", o])
+    objs.append(o)
+    if request.param == "kernel-arithmetic":
+        o = os.path.join(d, "fake_device_arith.cpp.o")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"] + inc +
+                              ["-c", os.path.join(ROOT, "tests", "fake_device_arith.cpp"), "-o", o])
+        so = os.path.join(d, "libhost_on_device_arith.so")
+        subprocess.check_call(["g++", "-shared", "-o", so] + objs + [o, "-Wl,--no-undefined"])
+    else:
+        import _simt_build
+        so = _simt_build.build(os.path.join(d, "simt"), extra_sources=[os.path.join(ROOT, "tests", "fake_device_simt.cpp")],
+                               extra_objects=objs, name="libhost_on_simt_kernels.so")
     L = C.CDLL(so)
+    L.kind = request.param
     L.fake_ctx_create.restype = C.c_void_p
-    L.fake_ctx_create.argtypes = [C.c_uint64, C.c_uint64, dp, dp, dp]
+    L.fake_ctx_create.argtypes = [C.c_uint64, C.c_uint64, dp, dp, dp] + ([C.c_int] if L.kind != "kernel-arithmetic" else [])
     L.fake_ctx_destroy.argtypes = [C.c_void_p]
     L.fake_ctx_get.argtypes = [C.c_void_p, dp, dp]
     L.fake_ctx_set_freq.argtypes = [C.c_void_p, dp]
     L.fake_ctx_viterbi.argtypes = [C.c_void_p, C.c_void_p]
-    L.fake_ctx_freq_passes.restype = C.c_uint64
-    L.fake_ctx_freq_passes.argtypes = [C.c_void_p]
     L.nfh_set_ind_params.argtypes = [C.c_void_p, dp, dp]
     L.nfh_host_em_iteration.restype = C.c_int
     L.nfh_host_em_iteration.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
@@ -67,13 +76,16 @@ def _p(a):
 class FakeRun:
     """The calls tests/test_gpu_golden.py makes on Context / EmRank / run_em, on the fake device."""
 
-    def __init__(self, lib, gl_norm, dist, freq, freq_est=1):
+    def __init__(self, lib, gl_norm, dist, freq, freq_est=1, freq_kernels=False):
+        """freq_kernels (emulator only): the frequency EM runs on the emulated kernels too - minutes per thousand
+        sites, so only the one-iteration fixtures ask for it; else on the kernels' arithmetic compiled for the host."""
         self.L = lib
         self.N, self.S, _ = gl_norm.shape
         gl_site = np.ascontiguousarray(np.transpose(gl_norm, (1, 0, 2)), dtype=np.float64)
         self.dist = np.ascontiguousarray(dist, dtype=np.float64)
         f = np.broadcast_to(np.asarray(freq, dtype=np.float64), (self.S,)).copy()
-        self.h = lib.fake_ctx_create(self.N, self.S, _p(gl_site), _p(self.dist), _p(f))
+        extra = [int(freq_kernels)] if lib.kind != "kernel-arithmetic" else []
+        self.h = lib.fake_ctx_create(self.N, self.S, _p(gl_site), _p(self.dist), _p(f), *extra)
         assert self.h
         self.freq_est = freq_est
 
@@ -134,7 +146,7 @@ def test_one_em_iteration_matches_reference_fixture(lib, path):
     g = {k: v for k, v in np.load(path).items()}
     S, N, _ = g["log_gl"].shape
     F = np.full(N, float(g["F0"])); a = np.full(N, float(g["a0"]))
-    run = FakeRun(lib, g["gl_norm"], g["dist_mb"], float(g["freq0"]))
+    run = FakeRun(lib, g["gl_norm"], g["dist_mb"], float(g["freq0"]), freq_kernels=True)
     try:
         lk, fr = run.iteration(F, a)
         np.testing.assert_allclose(lk, g["ind_lkl"], rtol=1e-9, atol=0)
