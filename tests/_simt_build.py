@@ -125,7 +125,7 @@ def build(scratch, flags=("-ffp-contract=off",), extra_sources=(), extra_objects
     `extra_objects`); returns the shared library's path."""
     os.makedirs(scratch, exist_ok=True)
     for f in sorted(os.listdir(CSRC)):
-        if not f.endswith((".cu", ".cuh", ".h")) or f in ("nfh_tma.cuh", "nfh_ctx.cu"):
+        if not f.endswith((".cu", ".cuh", ".h")) or f == "nfh_tma.cuh":
             continue
         text = open(os.path.join(CSRC, f)).read()
         open(os.path.join(scratch, f), "w").write(transform(f, text))
@@ -137,3 +137,30 @@ def build(scratch, flags=("-ffp-contract=off",), extra_sources=(), extra_objects
           list(extra_sources) + list(extra_objects) + ["-Wl,--no-undefined"]
     subprocess.check_call(cmd)
     return so
+
+
+def build_whole_product(scratch):
+    """The whole product for the emulator, in `scratch`: libngsfhmm_b200.so (kernels + launchers + nfh_ctx.cu),
+    libngsfhmm_host.so and the ngsF-HMM binary from the product's host sources, linked as host/Makefile links them."""
+    os.makedirs(scratch, exist_ok=True)
+    src = os.path.join(scratch, "src")
+    os.makedirs(src, exist_ok=True)
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh", ".h")) and f != "nfh_tma.cuh":
+            open(os.path.join(src, f), "w").write(transform(f, open(os.path.join(CSRC, f)).read()))
+    inc = os.path.join(ROOT, "include")
+    cuda_so = os.path.join(scratch, "libngsfhmm_b200.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I", src, "-I", SIMT,
+                           "-I", inc, "-o", cuda_so, os.path.join(SIMT, "libngsfhmm_b200_emulated.cpp"),
+                           os.path.join(SIMT, "simt.cpp"), "-lpthread"])
+    host = os.path.join(ROOT, "ngsf-hmm_b200", "host")
+    flags = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-I", host]
+    host_so = os.path.join(scratch, "libngsfhmm_host.so")
+    subprocess.check_call(["g++"] + flags + ["-shared", "-o", host_so] +
+                          [os.path.join(host, f) for f in ("lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp", "group.cpp")] +
+                          ["-L", scratch, "-lngsfhmm_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    cli = os.path.join(scratch, "ngsF-HMM")
+    cli_src = sorted(os.path.join(host, "cli", f) for f in os.listdir(os.path.join(host, "cli")) if f.endswith(".cpp"))
+    subprocess.check_call(["g++"] + flags + ["-o", cli] + cli_src +
+                          ["-L", scratch, "-lngsfhmm_host", "-lngsfhmm_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    return cuda_so, host_so, cli

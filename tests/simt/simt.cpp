@@ -1,8 +1,15 @@
 // simt.cpp - the fiber scheduler of tests/simt/simt.h (TEST INFRASTRUCTURE ONLY).
 #include "simt.h"
 
-uint3 threadIdx, blockIdx;
-dim3 blockDim, gridDim;
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+
+static int env_int(const char *name, int fallback) {
+  const char *v = std::getenv(name);
+  return v && *v ? std::atoi(v) : fallback;
+}
+int simt_device_count() { return env_int("SIMT_DEVICES", 1); }
+int simt_sm_count() { return env_int("SIMT_SMS", 4); }
 
 // Fiber switch.  swapcontext() makes a sigprocmask system call per switch, and an emulated EM run switches fibers a
 // few hundred million times; on x86-64 the switch is done by hand instead: push the callee-saved registers, swap the
@@ -36,9 +43,10 @@ simt_switch:
 
 namespace simt {
 
-static Cta g_cta;
-static unsigned long long g_launches = 0, g_switches = 0;
-alignas(1024) static unsigned char g_dyn_smem[256 * 1024];
+// all emulator state is per host thread: several host threads may each run kernels (one "rank" each)
+static thread_local Cta g_cta;
+static thread_local unsigned long long g_launches = 0, g_switches = 0;
+alignas(1024) static thread_local unsigned char g_dyn_smem[256 * 1024];
 constexpr size_t kStackBytes = 256 * 1024;
 
 Cta &cta() { return g_cta; }

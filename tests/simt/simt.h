@@ -29,7 +29,7 @@
 #define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __shared__ static
+#define __shared__ static thread_local     // one emulated CTA at a time PER HOST THREAD (host/group.cpp drives ranks from threads)
 #define __align__(n) alignas(n)
 #define NFH_DEV static inline
 #define NFH_DEV_TABLE static const
@@ -99,8 +99,10 @@ static inline cudaError_t cudaGetDriverEntryPoint(const char *name, void **fn, i
   return cudaSuccess;
 }
 
-extern uint3 threadIdx, blockIdx;
-extern dim3 blockDim, gridDim;
+#include "simt_runtime.h"
+
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
 
 using std::max;
 using std::min;
@@ -163,7 +165,7 @@ inline void syncwarp() {
 }
 inline void named_barrier(int id, int n_threads) {                       // bar.sync id, n_threads
   struct Named { int arrived = 0; unsigned gen = 0; };
-  static Named bars[16];
+  static thread_local Named bars[16];
   Named &b = bars[id & 15];
   const unsigned gen = b.gen;
   if (++b.arrived >= n_threads) { b.arrived = 0; b.gen++; return; }
