@@ -163,4 +163,13 @@ def build_whole_product(scratch):
     cli_src = sorted(os.path.join(host, "cli", f) for f in os.listdir(os.path.join(host, "cli")) if f.endswith(".cpp"))
     subprocess.check_call(["g++"] + flags + ["-o", cli] + cli_src +
                           ["-L", scratch, "-lngsfhmm_host", "-lngsfhmm_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"])
+    # the reference's own objects with iter_EM / viterbi overridden through the C ABI
+    # (oracle/Makefile, target `patched`), linked against the emulated library instead of the real one
+    obj = os.path.join(ROOT, "oracle", "_ref", "obj")
+    need = ["EM_weak.o", "HMM_weak.o", "b200_patch.o", "ngsF-HMM.o"]
+    if all(os.path.exists(os.path.join(obj, f)) for f in need):
+        rest = sorted(f for f in os.listdir(obj) if f.endswith(".o") and f not in need + ["EM.o", "HMM.o", "ref_harness.o"])
+        subprocess.check_call(["g++", "-O3"] + [os.path.join(obj, f) for f in rest + need] +
+                              ["-L", scratch, "-lngsfhmm_host", "-lngsfhmm_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN",
+                               "-o", os.path.join(scratch, "ngsF-HMM_b200patch")])
     return cuda_so, host_so, cli

@@ -19,3 +19,5 @@ def pytest_collection_finish(session):
         m = sys.modules.get(name)
         if m is not None and hasattr(m, "OURS"):
             m.OURS = os.path.join(DIR, "ngsF-HMM")
+        if m is not None and hasattr(m, "PATCHED") and os.path.exists(os.path.join(DIR, "ngsF-HMM_b200patch")):
+            m.PATCHED = os.path.join(DIR, "ngsF-HMM_b200patch")
