@@ -139,7 +139,7 @@ def build(scratch, flags=("-ffp-contract=off",), extra_sources=(), extra_objects
     return so
 
 
-def build_whole_product(scratch):
+def build_whole_product(scratch, opt="-O1"):
     """The whole product for the emulator, in `scratch`: libngsfhmm_b200.so (kernels + launchers + nfh_ctx.cu),
     libngsfhmm_host.so and the ngsF-HMM binary from the product's host sources, linked as host/Makefile links them."""
     os.makedirs(scratch, exist_ok=True)
@@ -150,7 +150,7 @@ def build_whole_product(scratch):
             open(os.path.join(src, f), "w").write(transform(f, open(os.path.join(CSRC, f)).read()))
     inc = os.path.join(ROOT, "include")
     cuda_so = os.path.join(scratch, "libngsfhmm_b200.so")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I", src, "-I", SIMT,
+    subprocess.check_call(["g++", opt, "-std=c++17", "-fPIC", "-shared", "-w", "-ffp-contract=off", "-I", src, "-I", SIMT,
                            "-I", inc, "-o", cuda_so, os.path.join(SIMT, "libngsfhmm_b200_emulated.cpp"),
                            os.path.join(SIMT, "simt.cpp"), "-lpthread"])
     host = os.path.join(ROOT, "ngsf-hmm_b200", "host")

@@ -35,7 +35,8 @@ def main():
     args = sys.argv[1:]
     if not any(a == "-k" for a in args):
         args = ["-k", " and ".join(f"not {t}" for t in TOO_BIG)] + args
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-p", "emulated_plugin", "-q",
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-o", "python_files=test_*.py emulated_cases.py",
+           "-m", "gpu", "-p", "emulated_plugin", "-q",
            "--durations=15"] + args
     return subprocess.call(cmd, env=env, cwd=ROOT)
 

@@ -182,6 +182,9 @@ def test_full_em_config1_shape_with_adjudication(lib, oracle):
     convergence) with the rule of tests/test_gpu_golden.py: alpha and frequencies 1e-6 against the reference outright;
     at least 16 of 20 F within 1e-6 of the reference, every exception within 1e-6 of the EM rerun with a long-double
     objective AND at a long-double likelihood no lower than the reference's."""
+    if lib.kind == "kernel-arithmetic":
+        pytest.skip("run once, on the stronger of the two fake devices (the kernels under the emulator); the sequential "
+                    "arithmetic gives the same 16 / 20 split in 17 s")
     g = {k: v for k, v in np.load(os.path.join(HERE, "golden", "em_cfg1_adjudication.npz")).items()}
     N, S = int(g["n_ind"]), int(g["n_sites"])
     d = sim.simulate(N, S, seed=int(g["seed"]), freq=0.2, indF=0.5, alpha=0.01, depth=2.0)
