@@ -102,6 +102,20 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
   const unsigned n = block.x * block.y * block.z;
   if (n == 0 || n > 1024 || dyn_smem_bytes > sizeof(g_dyn_smem)) { std::fprintf(stderr, "simt: bad launch\n"); std::abort(); }
   g_launches++;
+  // SIMT_ORDER: the order in which the scheduler resumes the fibers of a CTA in every round - "forward" (thread 0
+  // first, the default), "reverse", or "random:<seed>".  Results must not depend on it: a fiber runs undisturbed
+  // between two rendezvous points, so a different order is a different legal interleaving of the CTA's threads at
+  // barrier granularity, and a missing barrier (a read that only works because thread 0 happened to run first) shows
+  // up as a changed result or a deadlock.
+  int order_mode = 0;
+  static thread_local uint64_t rng = 0;
+  if (const char *o = std::getenv("SIMT_ORDER")) {
+    if (!std::strcmp(o, "reverse")) order_mode = 1;
+    else if (!std::strncmp(o, "random:", 7)) { order_mode = 2; if (!rng) rng = 0x9e3779b97f4a7c15ull ^ std::strtoull(o + 7, nullptr, 10); }
+  }
+  auto next_random = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+  std::vector<unsigned> order(n);
+  for (unsigned t = 0; t < n; t++) order[t] = order_mode == 1 ? n - 1 - t : t;
   if (c.stacks.size() < (size_t) n * kStackBytes) c.stacks.resize((size_t) n * kStackBytes);
   c.fibers.resize(n);
   c.n_threads = n;
@@ -143,7 +157,10 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
         while (remaining) {
           const unsigned long long before = g_switches;
           unsigned finished_now = 0;
-          for (unsigned t = 0; t < n; t++) {
+          if (order_mode == 2)                          // a fresh permutation every round
+            for (unsigned k = n - 1; k > 0; k--) std::swap(order[k], order[next_random() % (k + 1)]);
+          for (unsigned k = 0; k < n; k++) {
+            const unsigned t = order[k];
             if (c.fibers[t].done) continue;
             set_thread(t);
             to_fiber(t);

@@ -487,6 +487,37 @@ def test_one_em_iteration_of_kernels(oracle, kernels):
     _posterior_check(post2, marg2)
 
 
+def test_results_do_not_depend_on_the_order_threads_run_in(oracle, kernels, monkeypatch):
+    """The scheduler resumes a CTA's fibers thread 0 first by default.  Reversed and in a fresh random permutation
+    every round (SIMT_ORDER) every kernel family must give the same bits: a fiber runs undisturbed between two
+    rendezvous points, so another order is another legal interleaving at barrier granularity, and a missing
+    barrier - a read that only works because thread 0 happened to run first - would change a result or deadlock.
+    (The whole file also passes with SIMT_ORDER=reverse / random:<seed> set from outside.)"""
+    d, e = _case(oracle, 3, 4500, 77, freq=(0.05, 0.5), indF=(0.0, 0.5))
+    d.dist_mb[4300] = np.inf
+    F = np.array([0.1, 0.4, 0.02]); a = np.array([0.05, 1.0, 3.0])
+    gl_ind, post_in = _freq_case(oracle, 40, 48, 78)
+    gl_big, post_big = _freq_case(oracle, 600, 8, 79)
+    ind = [0, 0, 0, 1, 1, 2]; Fs = [0.1, 0.1 + 4e-6, 0.1, 0.4, 0.4, 0.02]; As = [0.05, 0.05, 0.05 + 4e-6, 1.0, 1.1, 3.0]
+    runs = {}
+    for order in ("forward", "reverse", "random:3", "random:11"):
+        monkeypatch.setenv("SIMT_ORDER", order)
+        with Ctx(kernels, e, d.dist_mb) as ctx:
+            ctx.set_params(F, a)
+            st, lk, post = ctx.estep()
+            obj, st2, lk2, post2 = ctx.lkl_batch(ind, Fs, As, with_estep=False), 0, None, None
+            path = ctx.viterbi()
+        with FreqSide(kernels, gl_ind) as fs:
+            f1 = fs.run(post=post_in)
+        with FreqSide(kernels, gl_big) as fs:
+            f2 = fs.run(post=post_big)
+        assert st == 0
+        runs[order] = [lk, post, obj, path, f1["freq"], f1["ratio"], f1["loge0"], f2["freq"], f2["ratio"], f2["loge0"]]
+    for order, got in runs.items():
+        for x, y in zip(got, runs["forward"]):
+            np.testing.assert_array_equal(x, y, err_msg=order)
+
+
 def test_product_does_not_know_the_emulator():
     """A checker, not a code path: nothing the product builds or loads mentions the emulator or its build."""
     import os
