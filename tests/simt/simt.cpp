@@ -71,6 +71,30 @@ static inline void to_fiber(unsigned t) {
 #endif
 }
 
+static thread_local std::vector<PendingCopy> g_loads, g_stores;
+std::vector<PendingCopy> &pending_loads() { return g_loads; }
+std::vector<PendingCopy> &pending_stores() { return g_stores; }
+void flush_loads(uint64_t *bar) {
+  for (size_t i = 0; i < g_loads.size();) {
+    if (g_loads[i].bar == bar) {
+      const std::function<void()> run = g_loads[i].run;
+      g_loads.erase(g_loads.begin() + (long) i);
+      run();
+    } else {
+      i++;
+    }
+  }
+}
+void flush_stores() {
+  std::vector<PendingCopy> todo;
+  todo.swap(g_stores);
+  for (auto &c : todo) c.run();
+}
+void poison(void *p, size_t bytes) {
+  const uint64_t nan = 0x7ff8dead0000beefull;      // a quiet NaN: any arithmetic on it stays NaN and raises the kernels' flag
+  for (size_t i = 0; i + 8 <= bytes; i += 8) std::memcpy((char *) p + i, &nan, 8);
+}
+
 void yield() {
   g_switches++;
   to_scheduler();
@@ -171,6 +195,9 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
           if (idle_rounds > 2000000ull) { std::fprintf(stderr, "simt: no progress in block (%u,%u) - deadlock?\n", bx, by); std::abort(); }
           (void) before;
         }
+        // a CTA may not end with a load nobody waited for; stores are drained as the hardware drains them at exit
+        if (!g_loads.empty()) { std::fprintf(stderr, "simt: block (%u,%u) ended with %zu bulk loads nobody waited for\n", bx, by, g_loads.size()); std::abort(); }
+        flush_stores();
       }
 }
 

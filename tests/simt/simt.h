@@ -147,6 +147,16 @@ Cta &cta();
 unsigned char *dyn_smem();                                           // 256 KB, 1024-byte aligned
 void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()> &kernel_call);
 void yield();
+// Asynchronous-copy model: a bulk copy issued by one thread is NOT performed at issue.  Its destination is poisoned
+// (NaN bit patterns) and the copy is queued; it happens when some thread waits on the copy's mbarrier (loads) or
+// calls tma_store_wait_read (stores).  Code that reads a tile before waiting, or reuses the source of a store
+// before wait_read, therefore computes with poison or stores the wrong bytes - as it may on the hardware.
+struct PendingCopy { void *dst; const void *src; uint32_t bytes; uint64_t *bar; std::function<void()> run; };
+std::vector<PendingCopy> &pending_loads();
+std::vector<PendingCopy> &pending_stores();
+void flush_loads(uint64_t *bar);
+void flush_stores();
+void poison(void *p, size_t bytes);
 unsigned long long launches();                                       // kernels launched so far
 unsigned long long switches();                                       // fiber switches so far
 
@@ -216,37 +226,46 @@ static inline void mbar_complete_tx(uint64_t *bar, uint32_t bytes) {
   *bar -= bytes;
   if ((*bar & 0x7fffffffffffffffull) == 0) *bar ^= 0x8000000000000000ull;       // phase completes
 }
-static inline void mbar_wait(uint64_t *bar, uint32_t parity) { while ((uint32_t) (*bar >> 63) == parity) simt::yield(); }
+static inline void mbar_wait(uint64_t *bar, uint32_t parity) {
+  simt::flush_loads(bar);                          // the copies of this barrier land now, not at issue
+  while ((uint32_t) (*bar >> 63) == parity) { simt::yield(); simt::flush_loads(bar); }
+}
 static inline void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   if (bytes % 16 || ((uintptr_t) smem_dst | (uintptr_t) gmem_src) % 16) { std::fprintf(stderr, "simt: misaligned bulk copy\n"); std::abort(); }
-  std::memcpy(smem_dst, gmem_src, bytes);
-  mbar_complete_tx(bar, bytes);
+  simt::poison(smem_dst, bytes);
+  simt::pending_loads().push_back({smem_dst, gmem_src, bytes, bar, [=]() {
+    std::memcpy(smem_dst, gmem_src, bytes);
+    mbar_complete_tx(bar, bytes);
+  }});
 }
 // box of box[1] rows x box[0] elements at element coordinates (x, y); out-of-bounds elements read as zero; with a
 // swizzle span the 16-byte chunk index inside each span-sized row is XORed with the row index modulo the number of
 // chunks (CU_TENSOR_MAP_SWIZZLE_32B / 64B / 128B for spans that equal the box row, as these maps use them)
 static inline void tma_load_2d(void *smem_dst, const void *tensor_map, int x, int y, uint64_t *bar) {
-  const CUtensorMap &m = *reinterpret_cast<const CUtensorMap *>(tensor_map);
+  const CUtensorMap m = *reinterpret_cast<const CUtensorMap *>(tensor_map);
   const uint32_t row_bytes = m.box[0] * m.elem_bytes;
   const uint32_t mask = m.swizzle_span ? m.swizzle_span / 16 - 1 : 0;
   if (m.swizzle_span && ((uintptr_t) smem_dst) % (8 * m.swizzle_span)) { std::fprintf(stderr, "simt: swizzled box not aligned to its pattern\n"); std::abort(); }
-  unsigned char *dst = reinterpret_cast<unsigned char *>(smem_dst);
-  for (uint32_t r = 0; r < m.box[1]; r++)
-    for (uint32_t c = 0; c < m.box[0]; c++) {
-      uint32_t off = r * row_bytes + c * m.elem_bytes;
-      off ^= ((off >> 7) & mask) << 4;
-      const int64_t gx = (int64_t) x + c, gy = (int64_t) y + r;
-      double v = 0.0;
-      if (gx >= 0 && gy >= 0 && (uint64_t) gx < m.dim[0] && (uint64_t) gy < m.dim[1])
-        std::memcpy(&v, m.base + (uint64_t) gy * m.row_stride + (uint64_t) gx * m.elem_bytes, 8);
-      std::memcpy(dst + off, &v, 8);
-    }
-  mbar_complete_tx(bar, m.box[1] * row_bytes);
+  simt::poison(smem_dst, (size_t) m.box[1] * row_bytes);
+  simt::pending_loads().push_back({smem_dst, nullptr, m.box[1] * row_bytes, bar, [=]() {
+    unsigned char *dst = reinterpret_cast<unsigned char *>(smem_dst);
+    for (uint32_t r = 0; r < m.box[1]; r++)
+      for (uint32_t c = 0; c < m.box[0]; c++) {
+        uint32_t off = r * row_bytes + c * m.elem_bytes;
+        off ^= ((off >> 7) & mask) << 4;
+        const int64_t gx = (int64_t) x + c, gy = (int64_t) y + r;
+        double v = 0.0;
+        if (gx >= 0 && gy >= 0 && (uint64_t) gx < m.dim[0] && (uint64_t) gy < m.dim[1])
+          std::memcpy(&v, m.base + (uint64_t) gy * m.row_stride + (uint64_t) gx * m.elem_bytes, 8);
+        std::memcpy(dst + off, &v, 8);
+      }
+    mbar_complete_tx(bar, m.box[1] * row_bytes);
+  }});
 }
 static inline void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
   if (bytes % 16 || ((uintptr_t) smem_src | (uintptr_t) gmem_dst) % 16) { std::fprintf(stderr, "simt: misaligned bulk store\n"); std::abort(); }
-  std::memcpy(gmem_dst, smem_src, bytes);
+  simt::pending_stores().push_back({gmem_dst, smem_src, bytes, nullptr, [=]() { std::memcpy(gmem_dst, smem_src, bytes); }});
 }
-static inline void tma_store_wait_read() {}
+static inline void tma_store_wait_read() { simt::flush_stores(); }
 static inline void fence_async_shared() {}
 }  // namespace nfh

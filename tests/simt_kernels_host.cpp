@@ -293,3 +293,48 @@ void simt_geno_posterior(SimtFreq *c, const char *path, double *out) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Self-tests of the emulator: deliberately broken kernels, so that the checks above are known not to be vacuous.
+//   mode 0: correct - thread 0 issues the bulk copy, every thread waits on the mbarrier, then reads
+//   mode 1: reads the tile BEFORE waiting                       -> poison (NaN) in the output
+//   mode 2: no __syncthreads between a shared-memory write of the LAST thread and the read by thread 0
+//           -> the result depends on the order threads run in (SIMT_ORDER)
+//   mode 3: overwrites the source of a bulk store before tma_store_wait_read -> the wrong bytes arrive
+// ---------------------------------------------------------------------------------------------------------------
+namespace nfh {
+static void selftest_kernel(int mode, const double *src, double *out) {
+  alignas(128) __shared__ double tile[128];
+  alignas(8) __shared__ uint64_t bar;
+  __shared__ double mailbox;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); mailbox = -1.0; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, sizeof tile);
+    tma_load_1d(tile, src, sizeof tile, &bar);
+  }
+  double early = 0.0;
+  if (mode == 1) early = tile[threadIdx.x];                 // BUG: the copy has not been waited for
+  mbar_wait(&bar, 0);
+  double v = mode == 1 ? early : tile[threadIdx.x];
+  __syncthreads();
+  if (mode == 2) {
+    if (threadIdx.x == blockDim.x - 1) mailbox = 42.0;
+    /* BUG: no __syncthreads() here */
+    if (threadIdx.x == 0) v += mailbox;
+  }
+  __syncthreads();
+  tile[threadIdx.x] = 2.0 * v;
+  fence_async_shared();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tma_store_1d(out, tile, sizeof tile);
+    if (mode == 3) tile[5] = -7.0;                          // BUG: the store may not have read its source yet
+    tma_store_wait_read();
+  }
+}
+}  // namespace nfh
+
+extern "C" void simt_selftest(int mode, const double *src /* [128], 16-byte aligned */, double *out /* [128] */) {
+  simt::launch(dim3(1), dim3(128), 0, [&]() { nfh::selftest_kernel(mode, src, out); });
+}

@@ -49,6 +49,7 @@ class SimtKernels:
         L.simt_freq_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp,
                                     C.POINTER(C.c_ulonglong)]
         L.simt_geno_posterior.argtypes = [C.c_void_p, C.c_void_p, _dp]
+        L.simt_selftest.argtypes = [C.c_int, _dp, _dp]
         L.simt_freq_run_stream.restype = C.c_int
         L.simt_freq_run_stream.argtypes = [C.c_void_p, C.c_int, C.c_uint, _dp, _dp, _dp, C.POINTER(C.c_ulonglong)]
 
@@ -516,6 +517,38 @@ def test_results_do_not_depend_on_the_order_threads_run_in(oracle, kernels, monk
     for order, got in runs.items():
         for x, y in zip(got, runs["forward"]):
             np.testing.assert_array_equal(x, y, err_msg=order)
+
+
+def test_the_emulator_catches_what_it_is_supposed_to_catch(kernels, monkeypatch):
+    """Deliberately broken kernels (tests/simt_kernels_host.cpp::selftest_kernel): reading a tile before waiting on
+    its mbarrier computes with poison, a missing __syncthreads shows as a result that depends on SIMT_ORDER, and
+    reusing the source of a bulk store before tma_store_wait_read delivers the wrong bytes - so the kernel tests
+    above, which pass in every order under the same model, are not vacuous."""
+    import ctypes.util
+    libc = C.CDLL(ctypes.util.find_library("c"))
+    libc.aligned_alloc.restype = C.c_void_p
+    libc.aligned_alloc.argtypes = [C.c_size_t, C.c_size_t]
+    mem = libc.aligned_alloc(128, 2 * 128 * 8)
+    src = np.ctypeslib.as_array(C.cast(mem, _dp), shape=(256,))[:128]
+    out = np.ctypeslib.as_array(C.cast(mem, _dp), shape=(256,))[128:]
+    src[:] = np.arange(128) + 1.0
+
+    def run(mode, order="forward"):
+        monkeypatch.setenv("SIMT_ORDER", order)
+        out[:] = 0.0
+        kernels.lib.simt_selftest(mode, _p(src), _p(out))
+        return out.copy()
+
+    want = 2.0 * (np.arange(128) + 1.0)
+    for order in ("forward", "reverse", "random:2"):
+        np.testing.assert_array_equal(run(0, order), want)                  # the correct kernel: any order
+    assert np.isnan(run(1)).any()                                           # read before wait: poison
+    a, b = run(2, "forward"), run(2, "reverse")
+    assert a[0] != b[0] and {a[0], b[0]} == {2.0 * (1.0 - 1.0), 2.0 * (1.0 + 42.0)}   # order-dependent: missing barrier
+    broken = run(3)
+    assert broken[5] == -7.0 and want[5] == 12.0                            # the store read its source too late
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(mem)
 
 
 def test_product_does_not_know_the_emulator():
