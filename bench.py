@@ -327,8 +327,9 @@ def main():
     #     the same millisecond and the E-step + BFGS phase of most ranks stretches from 4.1 to 6.3 ms;
     #   "mixed" (posteriors by all-to-all, emission ratios by peer stores from the frequency kernel): best at 2 and 4
     #     GPUs (15.6 / 16.8 ms against 16.4 / - ) and the default there; not yet run at 8 (its first 8-rank run hung in
-    #     the self-check on the ranks that own no individual of the 11; fixed in bfgs_update_lockstep and covered by a
-    #     CPU test since, but there was no GPU time left to repeat it), so 8 ranks keep the all-to-alls until it has;
+    #     the self-check on the ranks that own no individual of the 11; fixed in bfgs_update_lockstep, covered by a
+    #     CPU test and by an emulated 8-rank run since - tests/simt/run_multi_rank_emulated.py - but there was no GPU
+    #     time left to TIME it), so 8 ranks keep the all-to-alls until it has been;
     #   fixed frequencies: nothing to exchange per iteration ("direct" = emission refresh by peer stores, once).
     # NFH_EXCHANGE=direct|mixed|nccl overrides (NFH_PEER_DIRECT=0/1 = nccl/direct is still honoured).
     mode = os.environ.get("NFH_EXCHANGE", "")

@@ -1,6 +1,15 @@
 // simt.cpp - the fiber scheduler of tests/simt/simt.h (TEST INFRASTRUCTURE ONLY).
 #include "simt.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
 thread_local uint3 threadIdx, blockIdx;
 thread_local dim3 blockDim, gridDim;
 
@@ -8,6 +17,79 @@ static int env_int(const char *name, int fallback) {
   const char *v = std::getenv(name);
   return v && *v ? std::atoi(v) : fallback;
 }
+// ---- "device" memory: host memory, or named shared-memory segments when SIMT_IPC=1 (see simt_runtime.h) -------------
+namespace {
+struct Segment { std::string name; size_t bytes; bool owner; };
+std::mutex g_mem_mu;
+std::map<void *, Segment> g_segments;        // mapped segments of this process: own allocations and opened peers
+unsigned long g_segment_counter = 0;
+bool ipc_mode() { static const bool on = env_int("SIMT_IPC", 0) != 0; return on; }
+void unlink_all() {
+  for (auto &kv : g_segments)
+    if (kv.second.owner) shm_unlink(kv.second.name.c_str());
+}
+}  // namespace
+
+void *simt_device_alloc(size_t bytes) {
+  bytes = (bytes + 4095) / 4096 * 4096;
+  if (bytes == 0) bytes = 4096;
+  if (!ipc_mode()) return std::aligned_alloc(4096, bytes);
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  static bool registered = false;
+  if (!registered) { registered = true; std::atexit(unlink_all); }
+  char name[64];
+  std::snprintf(name, sizeof name, "/nfh_simt_%ld_%lu", (long) getpid(), g_segment_counter++);
+  const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  if (ftruncate(fd, (off_t) bytes) != 0) { close(fd); shm_unlink(name); return nullptr; }
+  void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) { shm_unlink(name); return nullptr; }
+  g_segments[p] = Segment{name, bytes, true};
+  return p;
+}
+void simt_device_free(void *p) {
+  if (!p) return;
+  if (!ipc_mode()) { std::free(p); return; }
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  auto it = g_segments.find(p);
+  if (it == g_segments.end()) return;
+  munmap(p, it->second.bytes);
+  if (it->second.owner) shm_unlink(it->second.name.c_str());
+  g_segments.erase(it);
+}
+int simt_ipc_export(void *p, char name_out[64]) {
+  if (!ipc_mode()) { std::memcpy(name_out, &p, sizeof p); return 0; }          // same process: the pointer itself
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  auto it = g_segments.find(p);
+  if (it == g_segments.end() || it->second.name.size() >= 56) return 1;        // only whole allocations are exported
+  std::memset(name_out, 0, 64);
+  std::memcpy(name_out, it->second.name.c_str(), it->second.name.size());
+  std::memcpy(name_out + 56, &it->second.bytes, 8);
+  return 0;
+}
+void *simt_ipc_open(const char name[64]) {
+  if (!ipc_mode()) { void *p; std::memcpy(&p, name, sizeof p); return p; }
+  size_t bytes;
+  std::memcpy(&bytes, name + 56, 8);
+  const int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return nullptr;
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  g_segments[p] = Segment{std::string(name), bytes, false};
+  return p;
+}
+void simt_ipc_close(void *p) {
+  if (!ipc_mode()) return;
+  std::lock_guard<std::mutex> lock(g_mem_mu);
+  auto it = g_segments.find(p);
+  if (it == g_segments.end()) return;
+  munmap(p, it->second.bytes);
+  g_segments.erase(it);
+}
+
 int simt_device_count() { return env_int("SIMT_DEVICES", 1); }
 int simt_sm_count() { return env_int("SIMT_SMS", 4); }
 

@@ -27,12 +27,24 @@ static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < simt_devic
 static inline cudaError_t cudaDeviceGetAttribute(int *v, int attr, int) { *v = attr == cudaDevAttrMultiProcessorCount ? simt_sm_count() : 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+// "Device" memory.  Normally plain host memory; with SIMT_IPC=1 in the environment every allocation is a POSIX
+// shared-memory segment, so that cudaIpcGetMemHandle / cudaIpcOpenMemHandle work ACROSS PROCESSES (one emulated rank per
+// process under torch.distributed/gloo: tests/simt/run_multi_rank_emulated.py) - the kernels of one rank then store
+// into the windows of another exactly as they do over NVLink.
+void *simt_device_alloc(size_t bytes);                     // simt.cpp
+void simt_device_free(void *p);
+int simt_ipc_export(void *p, char name_out[64]);           // 0 = ok
+void *simt_ipc_open(const char name[64]);
+void simt_ipc_close(void *p);
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t bytes) {
+  *p = (T *) simt_device_alloc(bytes);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+static inline cudaError_t cudaFree(void *p) { simt_device_free(p); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t bytes) {
   *p = (T *) std::aligned_alloc(1024, (bytes + 1023) / 1024 * 1024);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
-static inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
 static inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
@@ -59,6 +71,6 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, con
   a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = nullptr; a->hostPointer = nullptr;
   return cudaSuccess;
 }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof *h); return simt_ipc_export(p, h->reserved) == 0 ? cudaSuccess : 1; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { *p = simt_ipc_open(h.reserved); return *p ? cudaSuccess : 1; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *p) { simt_ipc_close(p); return cudaSuccess; }
