@@ -13,7 +13,8 @@ loudly instead of testing stale text:
   * nfh_freq.cu: the named barrier of the team kernel (`bar.sync id, n`, inline PTX) -> simt::named_barrier; the FP64
     probe of bench.py is cut; the tensor maps are encoded by the product's own freq_tensor_maps() through an emulated
     cuTensorMapEncodeTiled and honoured by the emulator's tma_load_2d (box, out-of-bounds zero fill, swizzle)
-  * nfh_estep.cu: the single-launch variant (`estep_fused`, opt-in, inline PTX acquire / release) is cut out
+  * nfh_estep.cu: the inline PTX of the opt-in single-launch variant (`estep_fused`: acquire / release on cross-CTA
+    flags, bulk-store group wait) becomes plain memory operations - CTAs run one after the other here
 
 Nothing else changes: the kernels' bodies, their launchers and their launch geometry are the product's text.
 """
@@ -93,14 +94,17 @@ def transform(name, src):
         assert src.count(old) == 1
         src = src.replace(old, "#if 1")
     if name == "nfh_estep.cu":
-        # the opt-in single-launch variant: inline PTX (acquire / release, bulk-copy groups); not emulated
-        src = _cut(src, "// ---------------------------------------------------------------------------\n// Single-launch E-step.",
-                   "// ---------------------------------------------------------------------------\n// host-side launchers",
-                   "estep_fused section")
-        src = _cut(src, "static long env_long(", "void launch_estep(", "launch_estep_fused")
-        old = "  if (launch_estep_fused(a, st)) return;\n"
-        assert src.count(old) == 1
-        src = src.replace(old, "")
+        # the opt-in single-launch variant (estep_fused): its inline PTX - acquire loads / release stores / a release
+        # reduction on the cross-CTA flags, and the bulk-store group wait - becomes plain memory operations (CTAs run
+        # one after the other here, so the first CTA takes every ticket and never waits for another one)
+        for old, new in [
+                ('asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");', "v = *p;"),
+                ('asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");', "v = *p;"),
+                ('asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");', "*p = v;"),
+                ('asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p) : "memory");', "*p += 1;"),
+                ('asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");', "simt::flush_stores();")]:
+            assert src.count(old) == 1, old
+            src = src.replace(old, new)
         assert "asm" not in re.sub(r"//[^\n]*", "", src)
     if name == "nfh_freq.cu":
         old = 'asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(n_threads) : "memory");'
@@ -114,7 +118,7 @@ def transform(name, src):
         src = re.sub(r"__shared__ alignas\((\d+)\)", r"alignas(\1) __shared__", src)   # ISO order for `static`
         src, n_launch = rewrite_launches(src)
         src, n_smem = rewrite_dyn_smem(src)
-        expect = {"nfh_estep.cu": (3, 2), "nfh_lkl.cu": (2, 1), "nfh_viterbi.cu": (5, 2), "nfh_freq.cu": (11, 3)}.get(name)
+        expect = {"nfh_estep.cu": (4, 3), "nfh_lkl.cu": (2, 1), "nfh_viterbi.cu": (5, 2), "nfh_freq.cu": (11, 3)}.get(name)
         if expect:
             assert (n_launch, n_smem) == expect, (name, n_launch, n_smem)
     return src

@@ -7,7 +7,7 @@ builds the whole product for the SIMT emulator into a scratch directory (tests/_
 kernels + launchers + nfh_ctx.cu from mechanically rewritten copies, the host library and the ngsF-HMM binary from the
 product's host sources as they are) and runs the `-m gpu` tests against it through the same ctypes bindings and the
 same command line - minus the cases an emulator cannot afford (1e5 - 1e8 individual-sites take hours at ~1e4
-individual-site-passes per second) or that read device memory through torch.  What passes here has exercised the C ABI
+individual-site-passes per second), that read device memory through torch or that need a second real device.  What passes here has exercised the C ABI
 layer, the launch geometry, every kernel and the host side at HEAD; what only the hardware can show (real concurrency,
 the MUFU seed, NVLink peers, performance) is what the GPU run is for.  Not part of the default test run, not a
 backend: the package never loads this build.
@@ -22,7 +22,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 # too large for an emulator, or reading device memory through torch / needing real devices
 TOO_BIG = ["full_size_properties", "long_sequence", "stream", "emission_matches_oracle", "two_ranks_match_one_rank",
-           "one_rank_per_device", "single_launch_estep"]
+           "one_rank_per_device"]
 
 
 def main():

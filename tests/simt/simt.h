@@ -121,6 +121,10 @@ static inline double nfh_host_rcp_seed(double x) {
 }
 static inline int atomicOr(int *p, int v) { const int o = *p; *p = o | v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+static inline unsigned atomicCAS(unsigned *p, unsigned expect, unsigned v) { const unsigned o = *p; if (o == expect) *p = v; return o; }
+static inline void __threadfence() {}
+template <class T> static inline T __ldcg(const T *p) { return *p; }        // cache-global load: a plain load here
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 3; return cudaSuccess; }
 
 // ---- the emulator ---------------------------------------------------------------------------------------------
 namespace simt {
@@ -198,6 +202,7 @@ template <class T> inline T exchange(T v, int src_lane) {             // src_lan
 }  // namespace simt
 
 static inline void __syncthreads() { simt::syncthreads(); }
+static inline void __nanosleep(unsigned) { simt::yield(); }             // a polling thread lets the others run
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::syncwarp(); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return simt::exchange(v, src & 31); }
 template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int = 32) { return simt::exchange(v, (int) (threadIdx.x & 31) - (int) d); }
@@ -267,5 +272,10 @@ static inline void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t b
   simt::pending_stores().push_back({gmem_dst, smem_src, bytes, nullptr, [=]() { std::memcpy(gmem_dst, smem_src, bytes); }});
 }
 static inline void tma_store_wait_read() { simt::flush_stores(); }
+// L2 eviction hints of the single-launch E-step: no cache here
+static inline uint64_t l2_policy_evict_last() { return 0; }
+static inline uint64_t l2_policy_evict_first() { return 0; }
+static inline void tma_load_1d_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t) { tma_load_1d(smem_dst, gmem_src, bytes, bar); }
+static inline void tma_store_1d_hint(void *gmem_dst, const void *smem_src, uint32_t bytes, uint64_t) { tma_store_1d(gmem_dst, smem_src, bytes); }
 static inline void fence_async_shared() {}
 }  // namespace nfh
