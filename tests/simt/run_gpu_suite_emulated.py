@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 
 # too large for an emulator, or reading device memory through torch / needing real devices
-TOO_BIG = ["full_size_properties", "long_sequence", "stream", "emission_matches_oracle", "two_ranks_match_one_rank",
+TOO_BIG = ["full_size_properties", "stream", "emission_matches_oracle", "two_ranks_match_one_rank",
            "one_rank_per_device"]
 
 
