@@ -165,26 +165,31 @@ def build_whole_product(scratch, opt="-O1", freq_opt="-O1"):
             open(os.path.join(src, f), "w").write(transform(f, open(os.path.join(CSRC, f)).read()))
     inc = os.path.join(ROOT, "include")
     cuda_so = os.path.join(scratch, "libngsfhmm_b200.so")
-    # two translation units side by side: the frequency kernels (hundreds of instantiations: 47 s at -O1, 15 s at -O0)
-    # and everything else (4 s at -O1)
+    host = os.path.join(ROOT, "ngsf-hmm_b200", "host")
+    # every translation unit at once: the two units of the emulated library (the frequency kernels - hundreds of
+    # instantiations - are 47 s at -O1, 15 s at -O0; everything else 4 s), the emulator, and the product's host and
+    # command-line sources with the flags of host/Makefile
     common = ["-std=c++17", "-fPIC", "-c", "-w", "-ffp-contract=off", "-I", src, "-I", SIMT, "-I", inc]
+    hflags = ["-O2", "-std=c++17", "-fPIC", "-c", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-I", host]
     units = [("libngsfhmm_b200_emulated.cpp", opt), ("libngsfhmm_b200_emulated_freq.cpp", freq_opt), ("simt.cpp", opt)]
+    lib_src = ["lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp", "group.cpp"]
+    cli_src = sorted(f for f in os.listdir(os.path.join(host, "cli")) if f.endswith(".cpp"))
     procs = [(subprocess.Popen(["g++", o] + common + ["-o", os.path.join(scratch, u + ".o"), os.path.join(SIMT, u)]), u)
              for u, o in units]
+    procs += [(subprocess.Popen(["g++"] + hflags + ["-o", os.path.join(scratch, "host_" + f + ".o"), os.path.join(host, f)]), f)
+              for f in lib_src]
+    procs += [(subprocess.Popen(["g++"] + hflags + ["-o", os.path.join(scratch, "cli_" + f + ".o"),
+                                                    os.path.join(host, "cli", f)]), f) for f in cli_src]
     for pr, u in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, u)
     subprocess.check_call(["g++", "-shared", "-o", cuda_so] + [os.path.join(scratch, u + ".o") for u, _ in units] +
                           ["-lpthread"])
-    host = os.path.join(ROOT, "ngsf-hmm_b200", "host")
-    flags = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-ffp-contract=off", "-I", inc, "-I", host]
     host_so = os.path.join(scratch, "libngsfhmm_host.so")
-    subprocess.check_call(["g++"] + flags + ["-shared", "-o", host_so] +
-                          [os.path.join(host, f) for f in ("lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp", "group.cpp")] +
+    subprocess.check_call(["g++", "-shared", "-o", host_so] + [os.path.join(scratch, "host_" + f + ".o") for f in lib_src] +
                           ["-L", scratch, "-lngsfhmm_b200", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     cli = os.path.join(scratch, "ngsF-HMM")
-    cli_src = sorted(os.path.join(host, "cli", f) for f in os.listdir(os.path.join(host, "cli")) if f.endswith(".cpp"))
-    subprocess.check_call(["g++"] + flags + ["-o", cli] + cli_src +
+    subprocess.check_call(["g++", "-o", cli] + [os.path.join(scratch, "cli_" + f + ".o") for f in cli_src] +
                           ["-L", scratch, "-lngsfhmm_host", "-lngsfhmm_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"])
     # the reference's own objects with iter_EM / viterbi overridden through the C ABI
     # (oracle/Makefile, target `patched`), linked against the emulated library instead of the real one
