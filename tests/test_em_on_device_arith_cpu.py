@@ -35,16 +35,18 @@ def lib(request, tmp_path_factory):
     together sequentially, or (b) tests/fake_device_simt.cpp: the kernels themselves under the SIMT emulator."""
     d = str(tmp_path_factory.mktemp("host_on_device_arith"))
     inc = ["-I", os.path.join(ROOT, "include"), "-I", HOST, "-I", CSRC]
-    objs = []
+    jobs = []                                                                  # compiled side by side
     for src in ("lbfgsb.cpp", "bfgs_driver.cpp", "host_api.cpp"):              # the flags of host/Makefile
         o = os.path.join(d, src + ".o")
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"] + inc +
-                              ["-c", os.path.join(HOST, src), "-o", o])
-        objs.append(o)
+        jobs.append((subprocess.Popen(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"] + inc +
+                                      ["-c", os.path.join(HOST, src), "-o", o]), o))
     o = os.path.join(d, "device_arith_host.cpp.o")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas"] + inc +
-                          ["-c", os.path.join(ROOT, "tests", "device_arith_host.cpp"), "-o", o])
-    objs.append(o)
+    jobs.append((subprocess.Popen(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas"] + inc +
+                                  ["-c", os.path.join(ROOT, "tests", "device_arith_host.cpp"), "-o", o]), o))
+    objs = []
+    for pr, o in jobs:
+        assert pr.wait() == 0, o
+        objs.append(o)
     if request.param == "kernel-arithmetic":
         o = os.path.join(d, "fake_device_arith.cpp.o")
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off"] + inc +
